@@ -1,0 +1,153 @@
+/* polargpu.h -- C ABI of the B200-native batched polar-code decoding engine (libpolargpu.so).
+ *
+ * The reference (CHEBSB/PolarDecoding) has no library or FFI layer: each SC_x/SCL_x/CASCL_x/BP_x .c file is a
+ * program whose main() builds a frame, calls ONE decoder function on it and counts errors.  The
+ * entry points below are what a binding for that hot path would bind; each cites what it replaces:
+ *
+ *   pg_decode_llr        void SCdecode(double *y,int *u_hat)        /root/reference/SC_128.c:395  (SC_1024.c:434, SC_128_fag.c:410)
+ *                        void SCLdecode(double *y,int *u_hat)       /root/reference/SCL_1024.c:547 (SCL_128.c:508, SCL_128_fag.c:526)
+ *                        void CASCL(double *y,int *u_hat)           /root/reference/CASCL_1024_L8.c:601 (CASCL_128.c:539, CASCL_1024_sys.c:1125)
+ *                        void BP(double *y,int *u_hat)              /root/reference/BP_1024.c:372 (BP_128.c:334, BP_128_fag.c:349)
+ *                        void BPr(double *y,int *u_hat,int *u)      /root/reference/BPr_128.c:373 (pg_bpr_* below)
+ *                        -- batched: B frames per call instead of one, LLRs instead of (y, global std)
+ *   pg_channel           the encode + channel block of main()       /root/reference/SC_128.c:171-202, CASCL_1024_L8.c:245-292
+ *                        (Ranq1/normal, SC_128.c:236-267, replaced by counter-based Philox4x32-10)
+ *   pg_simulate          the Monte-Carlo loop of main()             /root/reference/SC_128.c:164-222, CASCL_1024_L8.c:234-312
+ *   pg_info_set          the information-set block of main()        /root/reference/SC_128.c:139-147
+ *
+ * Conventions: plain pointers and sizes, caller owns every buffer, the context owns device scratch.
+ * All functions return 0 on success or a negative pg_status; pg_last_error() gives the text.
+ * There is NO CPU fallback: without a usable CUDA device pg_create() fails with PG_ERR_NO_DEVICE.
+ * One context = one GPU + one stream; calls on one context must be serialised by the caller
+ * (like the reference's decoders, which use process-global state, a context is not re-entrant).
+ *
+ * Bit order: position p of a frame is code bit / graph row p of the reference's Lee graph
+ * (G = F^{(x)n}, no bit reversal).  The Kao-graph ("_fag") programs differ from the Lee programs only
+ * by an internal relabelling, so they map to the same calls.
+ * Packed bit vectors: bit p of a frame is bit (p & 31) of 32-bit word (p >> 5). */
+#ifndef POLARGPU_H
+#define POLARGPU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pg_ctx pg_ctx;
+
+enum pg_status {
+    PG_OK = 0,
+    PG_ERR_ARG = -1,        /* bad parameter */
+    PG_ERR_NO_DEVICE = -2,  /* no CUDA device / wrong architecture (sm_100 required) */
+    PG_ERR_CUDA = -3,       /* CUDA runtime error, see pg_last_error */
+    PG_ERR_NCCL = -4,       /* NCCL error */
+    PG_ERR_UNSUPPORTED = -5 /* parameter combination without a compiled kernel */
+};
+
+enum pg_decoder { PG_DEC_SC = 0, PG_DEC_SCL = 1, PG_DEC_CASCL = 2, PG_DEC_BP = 3 };
+enum pg_real { PG_REAL_F64 = 0, /* parity mode: bit-exact with the reference's double arithmetic */
+               PG_REAL_F32 = 1  /* throughput mode */ };
+enum pg_data { PG_DATA_PN63 = 0,  /* the reference's PN-63 payload, phase m = frame*(K%63) mod 63 (SC_128.c:126-138,180,214) */
+               PG_DATA_PHILOX = 1 /* random payload from the Philox stream */ };
+
+typedef struct pg_params {
+    int N;                 /* block length: 128 or 1024 (any power of two 32..1024) */
+    int K;                 /* payload bits */
+    int crc_bits;          /* r: 0, 6 (CASCL_128.c:18) or 24 (CASCL_1024_L8.c:19); <= 32 */
+    uint64_t crc_poly;     /* bit e set <=> D^e in g(D), incl. D^r and 1; see PG_CRC24_POLY / PG_CRC6_POLY */
+    int crc_systematic;    /* 0: w = v*g (CASCL_1024_L8.c:251-266); 1: parity-first systematic (CASCL_1024_sys.c:776-789) */
+    int decoder;           /* enum pg_decoder */
+    int list_size;         /* L: 1 (SC) or 2,4,8,16,32 */
+    int iter_max;          /* BP sweeps: 100 (BP_1024.c:16); ignored otherwise */
+    int bp_early_stop;     /* 1: stop a frame once a sweep leaves every message bit-identical (decisions unchanged) */
+    int real;              /* enum pg_real */
+    int data_mode;         /* enum pg_data */
+    int count_from;        /* first index of I[] that enters the error count: r for CASCL_1024_sys.c:821, else 0 */
+    int device;            /* CUDA device ordinal */
+    uint64_t seed;         /* Philox key */
+    int rank, nranks;      /* frame-space partition for pg_simulate (see there) */
+} pg_params;
+
+#define PG_CRC24_POLY 0x1B2B117ull /* D^24+D^23+D^21+D^20+D^17+D^15+D^13+D^12+D^8+D^4+D^2+D+1 */
+#define PG_CRC6_POLY 0x61ull       /* D^6+D^5+1 */
+
+/* counters of one Eb/N0 point; all u64 so that multi-rank sums cannot overflow */
+typedef struct pg_counters {
+    uint64_t frames;       /* "run" */
+    uint64_t err_blocks;   /* "error block" */
+    uint64_t err_bits;     /* "Error bit" */
+    uint64_t tie_frames;   /* list decoders: frames in which an exact PM tie straddled the list boundary ("Oops!", SCL_1024.c:621) */
+    uint64_t crc_fail;     /* CA-SCL: frames in which no path passed the CRC */
+    uint64_t bp_sweeps;    /* BP: sweeps executed, summed over frames */
+    uint64_t reserved[2];
+} pg_counters;
+
+/* fill *p with the defaults of one of the reference programs: "SC_128", "SC_1024", "SC_128_fag", "SCL_128",
+ * "SCL_1024", "SCL_128_fag", "CASCL_128", "CASCL_1024_L8", "CASCL_1024_sys", "BP_128", "BP_1024", "BP_128_fag", "BPr_128" */
+int pg_params_preset(pg_params *p, const char *program);
+
+int pg_create(const pg_params *p, pg_ctx **out);
+void pg_destroy(pg_ctx *ctx);
+const char *pg_last_error(const pg_ctx *ctx); /* ctx may be NULL: error of the last failed pg_create on this thread */
+
+/* information(+CRC) positions in reliability order I[0..K+r) and the membership mask inI[0..N) (either may be NULL) */
+int pg_info_set(const pg_ctx *ctx, int *I_out, uint8_t *inI_out);
+
+/* ---- streaming mode: decode B frames of caller-supplied LLRs -------------------------------------------
+ * llr      [B][N] row-major, natural bit order; element type by llr_is_f64 (converted to the context's
+ *          arithmetic type on the device).  HOST pointer (pinned or pageable); copied H2D inside the call.
+ * u_hat    [B][N] one byte per bit (0/1), HOST, may be NULL.
+ * flags    [B] per-frame: bit0 tie frame, bit1 no CRC pass; bits 8..15 BP sweeps executed. HOST, may be NULL. */
+int pg_decode_llr(pg_ctx *ctx, const void *llr, int llr_is_f64, size_t B, uint8_t *u_hat, uint32_t *flags);
+/* as pg_decode_llr, but the decisions come back packed ([B][N/32] words, HOST): 32x less device-to-host traffic */
+int pg_decode_llr_packed(pg_ctx *ctx, const void *llr, int llr_is_f64, size_t B, uint32_t *u_hat_packed, uint32_t *flags);
+/* same with DEVICE pointers and packed output (u_hat_packed: [B][N/32] words); no copies, asynchronous on the ctx stream */
+int pg_decode_llr_device(pg_ctx *ctx, const void *d_llr, int llr_is_f64, size_t B, uint32_t *d_u_hat_packed, uint32_t *d_flags);
+
+/* ---- fused channel: payload, CRC, polar encode, BPSK, AWGN, LLR for frames [first_frame, first_frame+B) ----
+ * Noise comes from Philox4x32-10 with key = seed and counter = (global frame index, position/4): the result for a
+ * frame does not depend on B, on the batch split or on the rank that produces it.
+ * llr_out [B][N] (context's arithmetic type: float or double), u_out [B][N] bytes; HOST pointers, may be NULL. */
+int pg_channel(pg_ctx *ctx, double ebn0_db, uint64_t first_frame, size_t B, void *llr_out, uint8_t *u_out);
+
+/* ---- Monte-Carlo point: channel + decode + on-device error count -------------------------------------
+ * Simulates frames first_frame + rank*chunk + i ... in rounds of nranks*chunk frames (chunk = frames one rank
+ * processes per round) until, over all ranks, at least target_err_blocks block errors were seen or max_frames
+ * frames were run (either limit may be 0 = unlimited, not both).  With exact_stop != 0 the counters are truncated at
+ * the frame, in global frame order, on which the target-th block error fell -- the reference's stopping rule
+ * (SC_128.c:169) -- otherwise whole rounds are counted.  With nranks > 1 every rank must make the same call; the
+ * per-round counters are combined with one NCCL all-reduce (pg_comm_init first).  out = global counters. */
+int pg_simulate(pg_ctx *ctx, double ebn0_db, uint64_t first_frame, uint64_t target_err_blocks, uint64_t max_frames,
+                int exact_stop, pg_counters *out);
+
+/* fixed-size batch, no stopping rule, no collective: frames [first_frame, first_frame+B) on this GPU; counters ADDED to *acc.
+ * frame_err (HOST, [B], may be NULL): per frame, number of wrong counted bits (0 = frame correct).  Used by bench and tests. */
+int pg_simulate_batch(pg_ctx *ctx, double ebn0_db, uint64_t first_frame, size_t B, pg_counters *acc, uint16_t *frame_err);
+
+/* ---- BPR statistic (BPr_128.c:418-568): per-stage hard decision + re-encode error counts -------------------
+ * Enables sampling at the given 1-based sweep counts (ns <= 8) for subsequent BP calls; E (HOST, ns x (n+1) u64) is read
+ * back with pg_bpr_read (sums since the last pg_bpr_reset). */
+int pg_bpr_config(pg_ctx *ctx, const int *sample_sweeps, int ns);
+int pg_bpr_read(pg_ctx *ctx, uint64_t *E);
+int pg_bpr_reset(pg_ctx *ctx);
+
+/* ---- multi-GPU: one process (or thread) per GPU; only counters are exchanged ---------------------------------
+ * pg_comm_unique_id fills 128 bytes (ncclUniqueId) on one rank; the caller distributes them (MPI, torch.distributed,
+ * a file ...) and every rank calls pg_comm_init(ctx, id).  rank/nranks come from pg_params. */
+int pg_comm_unique_id(void *id128);
+int pg_comm_init(pg_ctx *ctx, const void *id128);
+int pg_allreduce_counters(pg_ctx *ctx, pg_counters *c); /* in place, sum over ranks */
+
+/* ---- introspection for benches ------------------------------------------------------------------------ */
+int pg_sync(pg_ctx *ctx);                              /* cudaStreamSynchronize on the ctx stream */
+void *pg_stream(pg_ctx *ctx);                          /* the cudaStream_t the kernels are launched on */
+uint64_t pg_kernel_launches(const pg_ctx *ctx);        /* kernels launched by this context so far */
+/* device time (ms, CUDA events on the ctx stream) of the last decode kernel and of the last channel kernel */
+int pg_last_kernel_ms(pg_ctx *ctx, float *decode_ms, float *channel_ms);
+const char *pg_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

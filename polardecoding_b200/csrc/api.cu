@@ -1,0 +1,638 @@
+// C ABI of libpolargpu.so (see include/polargpu.h): context, buffers, batching, the Monte-Carlo loop with
+// the reference's stopping rule, and the counter exchange between ranks.  Host logic only -- every
+// arithmetic step of the hot path is in channel.cu / list_decode.cu / bp_decode.cu.  No CPU fallback.
+#include "../../include/polargpu.h"
+#include "../../include/polar_q_table.h"
+#include "engine.h"
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace polar;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool load(std::string &err)
+    {
+        if (handle) return true;
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *nm : names) {
+            handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (handle) break;
+        }
+        if (!handle) { err = std::string("dlopen libnccl failed: ") + dlerror(); return false; }
+        GetUniqueId = (decltype(GetUniqueId))dlsym(handle, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(handle, "ncclCommInitRank");
+        AllReduce = (decltype(AllReduce))dlsym(handle, "ncclAllReduce");
+        CommDestroy = (decltype(CommDestroy))dlsym(handle, "ncclCommDestroy");
+        GetErrorString = (decltype(GetErrorString))dlsym(handle, "ncclGetErrorString");
+        if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) { err = "libnccl lacks required symbols"; return false; }
+        return true;
+    }
+};
+NcclApi g_nccl;
+
+int ilog2(int v) { int k = 0; while ((1 << k) < v) k++; return k; }
+
+}  // namespace
+
+struct pg_ctx {
+    pg_params p;
+    int n = 0, W = 0, nI = 0;
+    bool f64 = false;
+    int sm_count = 0;
+    std::vector<int> I;
+    std::vector<uint8_t> inI;
+    CodeMasks masks;
+    std::string err;
+
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // channel start/stop, decode start/stop
+    bool ev_ch = false, ev_dec = false;
+    uint64_t launches = 0;
+
+    // device tables
+    uint16_t *d_I = nullptr;
+    uint32_t *d_crc_masks = nullptr, *d_crc_sys = nullptr;
+    unsigned long long *d_counters = nullptr, *d_queue = nullptr, *d_bpr = nullptr;
+    int bpr_ns = 0, bpr_samples[8] = {0};
+
+    // work buffers for `cap` frames
+    size_t cap = 0;
+    void *d_llr = nullptr;     // real
+    void *d_in = nullptr;      // staging for caller LLRs of the other type
+    uint32_t *d_truth = nullptr, *d_uhat = nullptr, *d_info = nullptr;
+    uint8_t *d_bytes = nullptr;
+    uint32_t *h_info = nullptr;             // pinned
+    unsigned long long *h_counters = nullptr;  // pinned, CNT_N
+    void *d_scratch = nullptr;
+    int grid = 0;
+    size_t chunk_max = 0;
+
+    ncclComm_t comm = nullptr;
+    unsigned long long *d_xchg = nullptr;  // nranks*CNT_N
+};
+
+#define CU(call)                                                                                 \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess) {                                                                 \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                       \
+            return PG_ERR_CUDA;                                                                  \
+        }                                                                                        \
+    } while (0)
+
+extern "C" const char *pg_version(void) { return "polargpu 0.1 (sm_100a)"; }
+
+extern "C" int pg_params_preset(pg_params *p, const char *prog)
+{
+    if (!p || !prog) return PG_ERR_ARG;
+    std::memset(p, 0, sizeof(*p));
+    p->list_size = 1;
+    p->real = PG_REAL_F32;
+    p->data_mode = PG_DATA_PN63;
+    p->seed = 1024;
+    p->nranks = 1;
+    const std::string s(prog);
+    auto code = [&](int N, int K, int r, uint64_t poly, int sys) { p->N = N; p->K = K; p->crc_bits = r; p->crc_poly = poly; p->crc_systematic = sys; };
+    if (s == "SC_128" || s == "SC_128_fag") { code(128, 64, 0, 0, 0); p->decoder = PG_DEC_SC; }
+    else if (s == "SC_1024") { code(1024, 512, 0, 0, 0); p->decoder = PG_DEC_SC; }
+    else if (s == "SCL_128" || s == "SCL_128_fag") { code(128, 64, 0, 0, 0); p->decoder = PG_DEC_SCL; p->list_size = 8; }
+    else if (s == "SCL_1024") { code(1024, 512, 0, 0, 0); p->decoder = PG_DEC_SCL; p->list_size = 8; }
+    else if (s == "CASCL_128") { code(128, 64, 6, PG_CRC6_POLY, 0); p->decoder = PG_DEC_CASCL; p->list_size = 8; }
+    else if (s == "CASCL_1024_L8") { code(1024, 512, 24, PG_CRC24_POLY, 0); p->decoder = PG_DEC_CASCL; p->list_size = 8; }
+    else if (s == "CASCL_1024_sys") { code(1024, 512, 24, PG_CRC24_POLY, 1); p->decoder = PG_DEC_CASCL; p->list_size = 8; p->count_from = 24; }
+    else if (s == "BP_128" || s == "BP_128_fag") { code(128, 64, 0, 0, 0); p->decoder = PG_DEC_BP; p->iter_max = 100; }
+    else if (s == "BP_1024") { code(1024, 512, 0, 0, 0); p->decoder = PG_DEC_BP; p->iter_max = 100; }
+    else if (s == "BPr_128") { code(128, 64, 0, 0, 0); p->decoder = PG_DEC_BP; p->iter_max = 90; }
+    else return PG_ERR_ARG;
+    return PG_OK;
+}
+
+static int build_code(pg_ctx *ctx)
+{
+    const pg_params &p = ctx->p;
+    ctx->n = ilog2(p.N);
+    ctx->W = p.N / 32;
+    ctx->nI = p.K + p.crc_bits;
+    std::vector<int> q;
+    for (int i = 0; i < POLAR_Q_TABLE_LEN; i++)
+        if (polar_q_table_1024[i] < p.N) q.push_back(polar_q_table_1024[i]);
+    ctx->I.resize(ctx->nI);
+    ctx->inI.assign(p.N, 0);
+    for (int i = 0; i < ctx->nI; i++) { ctx->I[i] = q[p.N - ctx->nI + i]; ctx->inI[ctx->I[i]] = 1; }  // SC_128.c:143-147
+    std::memset(&ctx->masks, 0, sizeof(ctx->masks));
+    for (int i = 0; i < ctx->nI; i++) {
+        const int pos = ctx->I[i];
+        ctx->masks.info[pos >> 5] |= 1u << (pos & 31);
+        if (i >= p.count_from) ctx->masks.cnt[pos >> 5] |= 1u << (pos & 31);
+    }
+    return PG_OK;
+}
+
+static void free_buffers(pg_ctx *ctx)
+{
+    cudaFree(ctx->d_llr); cudaFree(ctx->d_in); cudaFree(ctx->d_truth); cudaFree(ctx->d_uhat); cudaFree(ctx->d_info);
+    cudaFree(ctx->d_bytes);
+    if (ctx->h_info) cudaFreeHost(ctx->h_info);
+    ctx->d_llr = ctx->d_in = nullptr; ctx->d_truth = ctx->d_uhat = ctx->d_info = nullptr; ctx->d_bytes = nullptr; ctx->h_info = nullptr;
+    ctx->cap = 0;
+}
+
+static int ensure_capacity(pg_ctx *ctx, size_t frames)
+{
+    if (frames <= ctx->cap) return PG_OK;
+    free_buffers(ctx);
+    const size_t N = ctx->p.N, W = ctx->W;
+    CU(cudaMalloc(&ctx->d_llr, frames * N * (ctx->f64 ? 8 : 4)));
+    CU(cudaMalloc(&ctx->d_in, frames * N * (ctx->f64 ? 4 : 8)));
+    CU(cudaMalloc(&ctx->d_truth, frames * W * 4));
+    CU(cudaMalloc(&ctx->d_uhat, frames * W * 4));
+    CU(cudaMalloc(&ctx->d_info, frames * 4));
+    CU(cudaMalloc(&ctx->d_bytes, frames * N));
+    CU(cudaMallocHost(&ctx->h_info, frames * 4));
+    ctx->cap = frames;
+    return PG_OK;
+}
+
+extern "C" int pg_create(const pg_params *p, pg_ctx **out)
+{
+    if (!p || !out) return PG_ERR_ARG;
+    *out = nullptr;
+    auto fail = [&](int code, const std::string &msg) { g_create_error = msg; return code; };
+    if (p->N < 32 || p->N > 1024 || (p->N & (p->N - 1))) return fail(PG_ERR_ARG, "N must be a power of two in 32..1024");
+    if (p->K < 1 || p->crc_bits < 0 || p->crc_bits > 32 || p->K + p->crc_bits > p->N) return fail(PG_ERR_ARG, "bad K / crc_bits");
+    if (p->crc_bits > 0 && (((p->crc_poly >> p->crc_bits) & 1ull) == 0 || (p->crc_poly & 1ull) == 0)) return fail(PG_ERR_ARG, "crc_poly must contain D^r and 1");
+    if (p->decoder < PG_DEC_SC || p->decoder > PG_DEC_BP) return fail(PG_ERR_ARG, "bad decoder");
+    if (p->real != PG_REAL_F64 && p->real != PG_REAL_F32) return fail(PG_ERR_ARG, "bad real");
+    if (p->nranks < 1 || p->rank < 0 || p->rank >= p->nranks) return fail(PG_ERR_ARG, "bad rank/nranks");
+    const int L = (p->decoder == PG_DEC_SC) ? 1 : p->list_size;
+    if (p->decoder != PG_DEC_BP && (L < 1 || L > 32 || (L & (L - 1)))) return fail(PG_ERR_ARG, "list_size must be 1,2,4,8,16,32");
+    if ((p->decoder == PG_DEC_SCL || p->decoder == PG_DEC_CASCL) && L < 2) return fail(PG_ERR_ARG, "list decoders need list_size >= 2");
+    if (p->decoder == PG_DEC_CASCL && p->crc_bits == 0) return fail(PG_ERR_ARG, "CA-SCL needs a CRC");
+    if (p->decoder == PG_DEC_BP && (p->iter_max < 1 || p->N < 64)) return fail(PG_ERR_ARG, "BP needs iter_max >= 1 and N >= 64");
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail(PG_ERR_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    if (p->device < 0 || p->device >= ndev) return fail(PG_ERR_ARG, "bad device ordinal");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, p->device)) != cudaSuccess) return fail(PG_ERR_CUDA, cudaGetErrorString(e));
+    if (prop.major != 10) return fail(PG_ERR_NO_DEVICE, "kernels are built for sm_100a only; device is sm_" + std::to_string(prop.major * 10 + prop.minor));
+    if ((e = cudaSetDevice(p->device)) != cudaSuccess) return fail(PG_ERR_CUDA, cudaGetErrorString(e));
+
+    pg_ctx *ctx = new pg_ctx();
+    ctx->p = *p;
+    ctx->p.list_size = L;
+    ctx->f64 = (p->real == PG_REAL_F64);
+    ctx->sm_count = prop.multiProcessorCount;
+    build_code(ctx);
+    auto bail = [&](int code) { g_create_error = ctx->err; pg_destroy(ctx); return code; };
+#define CUC(call)                                                                                \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return bail(PG_ERR_CUDA); } \
+    } while (0)
+    CUC(cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking));
+    for (auto &ev : ctx->ev) CUC(cudaEventCreate(&ev));
+    // tables
+    {
+        std::vector<uint16_t> I16(ctx->I.begin(), ctx->I.end());
+        CUC(cudaMalloc(&ctx->d_I, sizeof(uint16_t) * std::max<size_t>(1, I16.size())));
+        CUC(cudaMemcpy(ctx->d_I, I16.data(), sizeof(uint16_t) * I16.size(), cudaMemcpyHostToDevice));
+        const int r = p->crc_bits;
+        if (r > 0) {
+            // rem[i] = D^i mod g(D) as an r-bit word
+            std::vector<uint32_t> rem(ctx->nI);
+            const uint64_t low = p->crc_poly & ((r == 64 ? 0 : (1ull << r)) - 1ull);
+            uint64_t cur = 1;
+            for (int i = 0; i < ctx->nI; i++) {
+                rem[i] = (uint32_t)cur;
+                cur <<= 1;
+                if ((cur >> r) & 1ull) cur = (cur & ((1ull << r) - 1ull)) ^ low;
+            }
+            // syndrome bit b = parity over positions p=I[i] with bit b of rem[i] set  (CRcheck, CASCL_1024_L8.c:569-598)
+            std::vector<uint32_t> masks((size_t)r * ctx->W, 0u);
+            for (int i = 0; i < ctx->nI; i++)
+                for (int b = 0; b < r; b++)
+                    if ((rem[i] >> b) & 1u) masks[(size_t)b * ctx->W + (ctx->I[i] >> 5)] |= 1u << (ctx->I[i] & 31);
+            CUC(cudaMalloc(&ctx->d_crc_masks, masks.size() * 4));
+            CUC(cudaMemcpy(ctx->d_crc_masks, masks.data(), masks.size() * 4, cudaMemcpyHostToDevice));
+            std::vector<uint32_t> sys(p->K);
+            for (int i = 0; i < p->K; i++) sys[i] = rem[r + i];  // D^(r+i) mod g: row i of Gc (CASCL_1024_sys.c:49-561)
+            CUC(cudaMalloc(&ctx->d_crc_sys, sys.size() * 4));
+            CUC(cudaMemcpy(ctx->d_crc_sys, sys.data(), sys.size() * 4, cudaMemcpyHostToDevice));
+        }
+    }
+    CUC(cudaMalloc(&ctx->d_counters, CNT_N * 8));
+    CUC(cudaMemset(ctx->d_counters, 0, CNT_N * 8));
+    CUC(cudaMalloc(&ctx->d_queue, 8));
+    CUC(cudaMalloc(&ctx->d_bpr, 8 * 16 * 8));
+    CUC(cudaMemset(ctx->d_bpr, 0, 8 * 16 * 8));
+    CUC(cudaMallocHost(&ctx->h_counters, CNT_N * 8));
+    CUC(cudaMalloc(&ctx->d_xchg, (size_t)p->nranks * CNT_N * 8));
+    // launch geometry
+    if (p->decoder == PG_DEC_BP) {
+        BpPlan bp;
+        cudaError_t pe = bp_plan(ctx->n, ctx->f64, &bp);
+        if (pe != cudaSuccess) { ctx->err = std::string("no BP kernel for this N: ") + cudaGetErrorString(pe); return bail(PG_ERR_UNSUPPORTED); }
+        if (bp.ctas_per_sm < 1) { ctx->err = "BP kernel does not fit on an SM"; return bail(PG_ERR_UNSUPPORTED); }
+        ctx->grid = ctx->sm_count * bp.ctas_per_sm;
+    } else {
+        ListPlan lp;
+        cudaError_t pe = list_plan(ctx->n, L, ctx->f64, &lp);
+        if (pe != cudaSuccess) { ctx->err = std::string("no list kernel for this (N, L): ") + cudaGetErrorString(pe); return bail(PG_ERR_UNSUPPORTED); }
+        if (lp.ctas_per_sm < 1) { ctx->err = "list kernel does not fit on an SM"; return bail(PG_ERR_UNSUPPORTED); }
+        ctx->grid = ctx->sm_count * lp.ctas_per_sm;
+        if (lp.scratch_per_cta) CUC(cudaMalloc(&ctx->d_scratch, lp.scratch_per_cta * (size_t)ctx->grid));
+    }
+    {
+        const char *env = getenv("POLARGPU_CHUNK");
+        size_t c = env ? (size_t)atoll(env) : ((size_t)1 << 26) / (size_t)p->N;
+        ctx->chunk_max = std::max<size_t>(c, 32);
+    }
+#undef CUC
+    *out = ctx;
+    return PG_OK;
+}
+
+extern "C" void pg_destroy(pg_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->p.device);
+    if (ctx->st) cudaStreamSynchronize(ctx->st);
+    if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+    free_buffers(ctx);
+    cudaFree(ctx->d_I); cudaFree(ctx->d_crc_masks); cudaFree(ctx->d_crc_sys); cudaFree(ctx->d_counters); cudaFree(ctx->d_queue);
+    cudaFree(ctx->d_bpr); cudaFree(ctx->d_scratch); cudaFree(ctx->d_xchg);
+    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->st) cudaStreamDestroy(ctx->st);
+    delete ctx;
+}
+
+extern "C" const char *pg_last_error(const pg_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int pg_info_set(const pg_ctx *ctx, int *I_out, uint8_t *inI_out)
+{
+    if (!ctx) return PG_ERR_ARG;
+    if (I_out) std::copy(ctx->I.begin(), ctx->I.end(), I_out);
+    if (inI_out) std::copy(ctx->inI.begin(), ctx->inI.end(), inI_out);
+    return PG_OK;
+}
+
+// ---------------------------------------------------------------- launches
+static int run_channel(pg_ctx *ctx, double ebn0_db, uint64_t first, size_t B, bool want_llr)
+{
+    ChannelArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.llr = want_llr ? ctx->d_llr : nullptr;
+    a.u_packed = ctx->d_truth;
+    a.I = ctx->d_I;
+    a.crc_sys = ctx->d_crc_sys;
+    a.first_frame = first; a.B = B;
+    a.crc_poly = ctx->p.crc_poly; a.seed = ctx->p.seed;
+    a.N = ctx->p.N; a.n = ctx->n; a.K = ctx->p.K; a.r = ctx->p.crc_bits; a.nI = ctx->nI;
+    a.crc_systematic = ctx->p.crc_systematic; a.data_mode = ctx->p.data_mode;
+    a.sigma_d = std::pow(10.0, ebn0_db / -20.0);  // SC_128.c:167
+    a.sigma_f = (float)a.sigma_d;
+    CU(cudaEventRecord(ctx->ev[0], ctx->st));
+    CU(launch_channel(a, ctx->f64, ctx->sm_count, ctx->st));
+    CU(cudaEventRecord(ctx->ev[1], ctx->st));
+    ctx->ev_ch = true;
+    ctx->launches++;
+    return PG_OK;
+}
+
+static int run_decode(pg_ctx *ctx, const void *d_llr, size_t B, const uint32_t *d_truth, uint32_t *d_uhat, uint32_t *d_info, bool count)
+{
+    const pg_params &p = ctx->p;
+    CU(cudaEventRecord(ctx->ev[2], ctx->st));
+    if (p.decoder == PG_DEC_BP) {
+        BpArgs a;
+        std::memset(&a, 0, sizeof(a));
+        a.llr = d_llr; a.truth = d_truth; a.u_hat = d_uhat; a.frame_info = d_info;
+        a.counters = count ? ctx->d_counters : nullptr;
+        a.queue = ctx->d_queue;
+        a.bpr_E = ctx->bpr_ns ? ctx->d_bpr : nullptr;
+        a.bpr_ns = ctx->bpr_ns;
+        std::memcpy(a.bpr_samples, ctx->bpr_samples, sizeof(a.bpr_samples));
+        a.B = B; a.iters = p.iter_max; a.early_stop = p.bp_early_stop;
+        a.m = ctx->masks;
+        CU(cudaMemsetAsync(ctx->d_queue, 0, 8, ctx->st));
+        const int grid = (int)std::min<size_t>((size_t)ctx->grid, B);
+        CU(launch_bp(a, ctx->n, ctx->f64, std::max(grid, 1), ctx->st));
+    } else {
+        ListArgs a;
+        std::memset(&a, 0, sizeof(a));
+        a.llr = d_llr; a.truth = d_truth; a.u_hat = d_uhat; a.frame_info = d_info;
+        a.counters = count ? ctx->d_counters : nullptr;
+        a.gscratch = ctx->d_scratch;
+        a.crc_masks = ctx->d_crc_masks;
+        a.B = B; a.r = p.crc_bits; a.use_crc = (p.decoder == PG_DEC_CASCL);
+        a.m = ctx->masks;
+        const size_t fpw = 32 / (size_t)p.list_size;
+        const size_t groups = (B + fpw - 1) / fpw;
+        const int grid = (int)std::min<size_t>((size_t)ctx->grid, groups);
+        CU(launch_list(a, ctx->n, p.list_size, ctx->f64, std::max(grid, 1), ctx->st));
+    }
+    CU(cudaEventRecord(ctx->ev[3], ctx->st));
+    ctx->ev_dec = true;
+    ctx->launches++;
+    return PG_OK;
+}
+
+extern "C" int pg_decode_llr_device(pg_ctx *ctx, const void *d_llr, int llr_is_f64, size_t B, uint32_t *d_u_hat_packed, uint32_t *d_flags)
+{
+    if (!ctx || !d_llr) return PG_ERR_ARG;
+    if (B == 0) return PG_OK;
+    CU(cudaSetDevice(ctx->p.device));
+    const void *src = d_llr;
+    if ((llr_is_f64 != 0) != ctx->f64) {
+        int rc = ensure_capacity(ctx, B);
+        if (rc) return rc;
+        CU(launch_convert_llr(d_llr, llr_is_f64 != 0, ctx->d_llr, ctx->f64, B * (size_t)ctx->p.N, ctx->st));
+        ctx->launches++;
+        src = ctx->d_llr;
+    }
+    return run_decode(ctx, src, B, nullptr, d_u_hat_packed, d_flags, false);
+}
+
+static int decode_host(pg_ctx *ctx, const void *llr, int llr_is_f64, size_t B, uint8_t *u_hat, uint32_t *u_hat_packed, uint32_t *flags)
+{
+    if (!ctx || !llr) return PG_ERR_ARG;
+    CU(cudaSetDevice(ctx->p.device));
+    const size_t N = ctx->p.N, W = ctx->W;
+    const size_t esz = llr_is_f64 ? 8 : 4;
+    const bool conv = (llr_is_f64 != 0) != ctx->f64;
+    for (size_t off = 0; off < B; off += ctx->chunk_max) {
+        const size_t b = std::min(ctx->chunk_max, B - off);
+        int rc = ensure_capacity(ctx, b);
+        if (rc) return rc;
+        void *dst = conv ? ctx->d_in : ctx->d_llr;
+        CU(cudaMemcpyAsync(dst, (const char *)llr + off * N * esz, b * N * esz, cudaMemcpyHostToDevice, ctx->st));
+        if (conv) { CU(launch_convert_llr(ctx->d_in, llr_is_f64 != 0, ctx->d_llr, ctx->f64, b * N, ctx->st)); ctx->launches++; }
+        rc = run_decode(ctx, ctx->d_llr, b, nullptr, ctx->d_uhat, ctx->d_info, false);
+        if (rc) return rc;
+        if (u_hat) {
+            CU(launch_unpack_bits(ctx->d_uhat, ctx->d_bytes, b, (int)N, ctx->st));
+            ctx->launches++;
+            CU(cudaMemcpyAsync(u_hat + off * N, ctx->d_bytes, b * N, cudaMemcpyDeviceToHost, ctx->st));
+        }
+        if (u_hat_packed) CU(cudaMemcpyAsync(u_hat_packed + off * W, ctx->d_uhat, b * W * 4, cudaMemcpyDeviceToHost, ctx->st));
+        if (flags) CU(cudaMemcpyAsync(flags + off, ctx->d_info, b * 4, cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaStreamSynchronize(ctx->st));
+    }
+    if (flags)
+        for (size_t i = 0; i < B; i++) flags[i] = ((flags[i] >> 16) & 3u) | ((flags[i] >> 24) << 8);
+    return PG_OK;
+}
+
+extern "C" int pg_decode_llr(pg_ctx *ctx, const void *llr, int llr_is_f64, size_t B, uint8_t *u_hat, uint32_t *flags)
+{
+    return decode_host(ctx, llr, llr_is_f64, B, u_hat, nullptr, flags);
+}
+
+extern "C" int pg_decode_llr_packed(pg_ctx *ctx, const void *llr, int llr_is_f64, size_t B, uint32_t *u_hat_packed, uint32_t *flags)
+{
+    return decode_host(ctx, llr, llr_is_f64, B, nullptr, u_hat_packed, flags);
+}
+
+extern "C" int pg_channel(pg_ctx *ctx, double ebn0_db, uint64_t first_frame, size_t B, void *llr_out, uint8_t *u_out)
+{
+    if (!ctx) return PG_ERR_ARG;
+    CU(cudaSetDevice(ctx->p.device));
+    const size_t N = ctx->p.N, esz = ctx->f64 ? 8 : 4;
+    for (size_t off = 0; off < B; off += ctx->chunk_max) {
+        const size_t b = std::min(ctx->chunk_max, B - off);
+        int rc = ensure_capacity(ctx, b);
+        if (rc) return rc;
+        rc = run_channel(ctx, ebn0_db, first_frame + off, b, true);
+        if (rc) return rc;
+        if (llr_out) CU(cudaMemcpyAsync((char *)llr_out + off * N * esz, ctx->d_llr, b * N * esz, cudaMemcpyDeviceToHost, ctx->st));
+        if (u_out) {
+            CU(launch_unpack_bits(ctx->d_truth, ctx->d_bytes, b, (int)N, ctx->st));
+            ctx->launches++;
+            CU(cudaMemcpyAsync(u_out + off * N, ctx->d_bytes, b * N, cudaMemcpyDeviceToHost, ctx->st));
+        }
+        CU(cudaStreamSynchronize(ctx->st));
+    }
+    return PG_OK;
+}
+
+// one chunk: channel + decode + count; leaves the chunk's counters (delta) in h_counters and frame_info in h_info (if wanted)
+static int simulate_chunk(pg_ctx *ctx, double ebn0_db, uint64_t first, size_t b, bool want_info)
+{
+    int rc = ensure_capacity(ctx, b);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(ctx->d_counters, 0, CNT_N * 8, ctx->st));
+    rc = run_channel(ctx, ebn0_db, first, b, true);
+    if (rc) return rc;
+    rc = run_decode(ctx, ctx->d_llr, b, ctx->d_truth, nullptr, ctx->d_info, true);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, CNT_N * 8, cudaMemcpyDeviceToHost, ctx->st));
+    if (want_info) CU(cudaMemcpyAsync(ctx->h_info, ctx->d_info, b * 4, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    return PG_OK;
+}
+
+static void add_counters(pg_counters *acc, const unsigned long long *c)
+{
+    acc->frames += c[CNT_FRAMES]; acc->err_blocks += c[CNT_ERR_BLOCKS]; acc->err_bits += c[CNT_ERR_BITS];
+    acc->tie_frames += c[CNT_TIE]; acc->crc_fail += c[CNT_CRCFAIL]; acc->bp_sweeps += c[CNT_SWEEPS];
+}
+
+extern "C" int pg_simulate_batch(pg_ctx *ctx, double ebn0_db, uint64_t first_frame, size_t B, pg_counters *acc, uint16_t *frame_err)
+{
+    if (!ctx || !acc) return PG_ERR_ARG;
+    CU(cudaSetDevice(ctx->p.device));
+    for (size_t off = 0; off < B; off += ctx->chunk_max) {
+        const size_t b = std::min(ctx->chunk_max, B - off);
+        int rc = simulate_chunk(ctx, ebn0_db, first_frame + off, b, frame_err != nullptr);
+        if (rc) return rc;
+        add_counters(acc, ctx->h_counters);
+        if (frame_err)
+            for (size_t i = 0; i < b; i++) frame_err[off + i] = (uint16_t)(ctx->h_info[i] & 0xFFFFu);
+    }
+    return PG_OK;
+}
+
+// sum-exchange of a small u64 vector over the ranks (identity for nranks == 1)
+static int exchange(pg_ctx *ctx, unsigned long long *host_vec, size_t count)
+{
+    if (ctx->p.nranks == 1) return PG_OK;
+    if (!ctx->comm) { ctx->err = "nranks > 1 but pg_comm_init was not called"; return PG_ERR_NCCL; }
+    CU(cudaMemcpyAsync(ctx->d_xchg, host_vec, count * 8, cudaMemcpyHostToDevice, ctx->st));
+    ncclResult_t r = g_nccl.AllReduce(ctx->d_xchg, ctx->d_xchg, count, ncclUint64, ncclSum, ctx->comm, ctx->st);
+    if (r != ncclSuccess) { ctx->err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"); return PG_ERR_NCCL; }
+    CU(cudaMemcpyAsync(host_vec, ctx->d_xchg, count * 8, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    return PG_OK;
+}
+
+extern "C" int pg_simulate(pg_ctx *ctx, double ebn0_db, uint64_t first_frame, uint64_t target_err_blocks, uint64_t max_frames,
+                           int exact_stop, pg_counters *out)
+{
+    if (!ctx || !out || (target_err_blocks == 0 && max_frames == 0)) return PG_ERR_ARG;
+    CU(cudaSetDevice(ctx->p.device));
+    const int R = ctx->p.nranks, me = ctx->p.rank;
+    std::memset(out, 0, sizeof(*out));
+    uint64_t next = first_frame;  // first global frame of the next round
+    size_t chunk = std::min<size_t>(ctx->chunk_max, 4096);
+    std::vector<unsigned long long> xc((size_t)R * CNT_N);
+    while (true) {
+        // frames of this round: rank q takes [next + q*chunk, next + (q+1)*chunk) clipped to the frame budget
+        uint64_t budget = max_frames ? (max_frames - out->frames) : ~0ull;
+        if (max_frames && budget == 0) break;
+        auto rank_count = [&](int q) -> size_t {
+            const uint64_t lo = (uint64_t)q * chunk;
+            if (lo >= budget) return 0;
+            return (size_t)std::min<uint64_t>(chunk, budget - lo);
+        };
+        const size_t mine = rank_count(me);
+        std::fill(xc.begin(), xc.end(), 0ull);
+        if (mine) {
+            int rc = simulate_chunk(ctx, ebn0_db, next + (uint64_t)me * chunk, mine, exact_stop != 0);
+            if (rc) return rc;
+            std::memcpy(&xc[(size_t)me * CNT_N], ctx->h_counters, CNT_N * 8);
+        }
+        int rc = exchange(ctx, xc.data(), xc.size());
+        if (rc) return rc;
+        // walk the ranks in global frame order
+        bool done = false;
+        for (int q = 0; q < R && !done; q++) {
+            const unsigned long long *c = &xc[(size_t)q * CNT_N];
+            if (exact_stop && target_err_blocks && out->err_blocks + c[CNT_ERR_BLOCKS] >= target_err_blocks) {
+                // the target-th block error falls into rank q's chunk: that rank truncates, everybody learns the result
+                unsigned long long part[CNT_N];
+                std::memset(part, 0, sizeof(part));
+                if (q == me) {
+                    const uint64_t need = target_err_blocks - out->err_blocks;
+                    uint64_t seen = 0;
+                    size_t i = 0;
+                    for (; i < mine && seen < need; i++) {
+                        const uint32_t w = ctx->h_info[i];
+                        part[CNT_FRAMES]++;
+                        if (w & 0xFFFFu) { part[CNT_ERR_BLOCKS]++; part[CNT_ERR_BITS] += (w & 0xFFFFu); seen++; }
+                        if (w & kInfoTie) part[CNT_TIE]++;
+                        if (w & kInfoCrcFail) part[CNT_CRCFAIL]++;
+                        part[CNT_SWEEPS] += (w >> 24);
+                    }
+                }
+                rc = exchange(ctx, part, CNT_N);
+                if (rc) return rc;
+                add_counters(out, part);
+                done = true;
+            } else {
+                add_counters(out, c);
+            }
+        }
+        if (done) break;
+        if (target_err_blocks && out->err_blocks >= target_err_blocks) break;
+        if (max_frames && out->frames >= max_frames) break;
+        next += (uint64_t)R * chunk;
+        if (chunk < ctx->chunk_max) chunk = std::min(ctx->chunk_max, chunk * 2);
+    }
+    return PG_OK;
+}
+
+// ---------------------------------------------------------------- BPR statistic
+extern "C" int pg_bpr_config(pg_ctx *ctx, const int *sample_sweeps, int ns)
+{
+    if (!ctx || ns < 0 || ns > 8 || (ns && !sample_sweeps)) return PG_ERR_ARG;
+    ctx->bpr_ns = ns;
+    for (int i = 0; i < ns; i++) ctx->bpr_samples[i] = sample_sweeps[i];
+    return pg_bpr_reset(ctx);
+}
+
+extern "C" int pg_bpr_read(pg_ctx *ctx, uint64_t *E)
+{
+    if (!ctx || !E) return PG_ERR_ARG;
+    CU(cudaSetDevice(ctx->p.device));
+    CU(cudaStreamSynchronize(ctx->st));
+    std::vector<unsigned long long> tmp(8 * 16);
+    CU(cudaMemcpy(tmp.data(), ctx->d_bpr, tmp.size() * 8, cudaMemcpyDeviceToHost));
+    for (int q = 0; q < ctx->bpr_ns; q++)
+        for (int s = 0; s <= ctx->n; s++) E[q * (ctx->n + 1) + s] = tmp[q * 16 + s];
+    return PG_OK;
+}
+
+extern "C" int pg_bpr_reset(pg_ctx *ctx)
+{
+    if (!ctx) return PG_ERR_ARG;
+    CU(cudaSetDevice(ctx->p.device));
+    CU(cudaMemsetAsync(ctx->d_bpr, 0, 8 * 16 * 8, ctx->st));
+    return PG_OK;
+}
+
+// ---------------------------------------------------------------- multi-GPU
+extern "C" int pg_comm_unique_id(void *id128)
+{
+    if (!id128) return PG_ERR_ARG;
+    std::string err;
+    if (!g_nccl.load(err)) { g_create_error = err; return PG_ERR_NCCL; }
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) { g_create_error = "ncclGetUniqueId failed"; return PG_ERR_NCCL; }
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    std::memcpy(id128, &id, 128);
+    return PG_OK;
+}
+
+extern "C" int pg_comm_init(pg_ctx *ctx, const void *id128)
+{
+    if (!ctx || !id128) return PG_ERR_ARG;
+    if (!g_nccl.load(ctx->err)) return PG_ERR_NCCL;
+    CU(cudaSetDevice(ctx->p.device));
+    ncclUniqueId id;
+    std::memcpy(&id, id128, 128);
+    ncclResult_t r = g_nccl.CommInitRank(&ctx->comm, ctx->p.nranks, id, ctx->p.rank);
+    if (r != ncclSuccess) { ctx->err = std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"); ctx->comm = nullptr; return PG_ERR_NCCL; }
+    return PG_OK;
+}
+
+extern "C" int pg_allreduce_counters(pg_ctx *ctx, pg_counters *c)
+{
+    if (!ctx || !c) return PG_ERR_ARG;
+    static_assert(sizeof(pg_counters) == CNT_N * 8, "pg_counters layout");
+    CU(cudaSetDevice(ctx->p.device));
+    return exchange(ctx, reinterpret_cast<unsigned long long *>(c), CNT_N);
+}
+
+// ---------------------------------------------------------------- introspection
+extern "C" int pg_sync(pg_ctx *ctx)
+{
+    if (!ctx) return PG_ERR_ARG;
+    CU(cudaSetDevice(ctx->p.device));
+    CU(cudaStreamSynchronize(ctx->st));
+    return PG_OK;
+}
+
+extern "C" void *pg_stream(pg_ctx *ctx) { return ctx ? (void *)ctx->st : nullptr; }
+extern "C" uint64_t pg_kernel_launches(const pg_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int pg_last_kernel_ms(pg_ctx *ctx, float *decode_ms, float *channel_ms)
+{
+    if (!ctx) return PG_ERR_ARG;
+    CU(cudaSetDevice(ctx->p.device));
+    CU(cudaStreamSynchronize(ctx->st));
+    if (decode_ms) { *decode_ms = 0; if (ctx->ev_dec) CU(cudaEventElapsedTime(decode_ms, ctx->ev[2], ctx->ev[3])); }
+    if (channel_ms) { *channel_ms = 0; if (ctx->ev_ch) CU(cudaEventElapsedTime(channel_ms, ctx->ev[0], ctx->ev[1])); }
+    return PG_OK;
+}

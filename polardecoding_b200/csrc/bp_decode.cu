@@ -1,0 +1,214 @@
+// Belief-propagation decoding on the polar factor graph, one frame per CTA, messages resident in
+// shared memory (sm_100a).
+//
+// What it computes (reference): BP() /root/reference/BP_1024.c:372-427 (BP_128.c:334, BP_128_fag.c:349):
+// iterMax round trips, each an R pass over stages 0..n-1 followed by an L pass over stages n-1..0, every
+// butterfly (j, j+2^s) updating
+//     r(s+1,j)   = CHK(r(s,j), l(s+1,j+d) + r(s,j+d))      r(s+1,j+d) = r(s,j+d) + CHK(r(s,j), l(s+1,j))
+//     l(s,j)     = CHK(l(s+1,j), l(s+1,j+d) + r(s,j+d))    l(s,j+d)   = l(s+1,j+d) + CHK(r(s,j), l(s+1,j))
+// with l(n,.) = channel LLR, r(0,.) = 999 on frozen positions and 0 elsewhere, decision l(0,j)+r(0,j) >= 0 -> 0.
+// BPr() /root/reference/BPr_128.c:373-580 adds the per-stage hard-decision statistic (optional, see bpr_*).
+//
+// How: the N/2 butterflies of a stage are independent, stages are sequential -> one butterfly (or two) per
+// thread per stage and a barrier between stages.  Only l(1..n-1) and r(1..n-1) are state ((n-1)*2*N values:
+// 72 KB in fp32 for N=1024, three frames resident per SM); l(n) lives in registers, r(0) is a bit mask.
+// Two stage passes of the reference produce values nobody reads -- r(n) (R pass, last stage) and, in every
+// sweep but the last, l(0) -- and are not executed; l(0) is formed once after the last sweep.
+// Fixed-point stop (optional): the sweep map is deterministic and r is a function of l, so once an L pass
+// leaves l(1..n-1) bit-identical the remaining sweeps cannot change anything; the frame then stops with the
+// decisions the full iterMax sweeps would give.  Frames are pulled from a device-side queue so CTAs that
+// finish early start the next frame.
+#include "engine.h"
+#include "polar_common.cuh"
+
+namespace polar {
+
+template <typename real, int LOGN, int THREADS>
+struct BpCfg {
+    static constexpr int N = 1 << LOGN;
+    static constexpr int W = (N + 31) / 32;
+    static constexpr int BPT = (N / 2) / THREADS;  // butterflies per thread per stage
+    static constexpr size_t MSG = (size_t)2 * (LOGN - 1) * N;  // l(1..n-1), r(1..n-1)
+    static constexpr size_t SMEM = MSG * sizeof(real) + (size_t)(W + 4) * 4;
+};
+
+template <int THREADS>
+__device__ __forceinline__ void cta_sync()
+{
+    if (THREADS == 32) __syncwarp();
+    else __syncthreads();
+}
+
+template <typename real, int LOGN, int THREADS>
+__global__ void __launch_bounds__(THREADS) bp_decode_kernel(const BpArgs a)
+{
+    using C = BpCfg<real, LOGN, THREADS>;
+    using RT = real_traits<real>;
+    constexpr int N = C::N, W = C::W, BPT = C::BPT, n = LOGN;
+    static_assert(BPT >= 1, "too many threads for this N");
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    real *Lm = reinterpret_cast<real *>(smem_raw);        // Lm[(s-1)*N + j] = l(s,j), s=1..n-1
+    real *Rm = Lm + (size_t)(n - 1) * N;                  // Rm[(s-1)*N + j] = r(s,j), s=1..n-1
+    uint32_t *uh = reinterpret_cast<uint32_t *>(smem_raw + C::MSG * sizeof(real));  // W words + [W]=nerr, [W+1]=frame lo, [W+2]=frame hi
+    const int tid = threadIdx.x;
+
+    auto r0 = [&](int j) -> real { return ((a.m.info[j >> 5] >> (j & 31)) & 1u) ? (real)0 : (real)999; };
+
+    for (;;) {
+        if (tid == 0) {
+            const unsigned long long f = atomicAdd(a.queue, 1ull);
+            uh[W + 1] = (uint32_t)f;
+            uh[W + 2] = (uint32_t)(f >> 32);
+        }
+        cta_sync<THREADS>();
+        const unsigned long long frame = (unsigned long long)uh[W + 1] | ((unsigned long long)uh[W + 2] << 32);
+        if (frame >= a.B) break;
+        const real *llr = reinterpret_cast<const real *>(a.llr) + frame * (size_t)N;
+
+        real ch_up[BPT], ch_lo[BPT];
+#pragma unroll
+        for (int i = 0; i < BPT; i++) {
+            const int q = tid + i * THREADS;
+            ch_up[i] = __ldg(llr + q);
+            ch_lo[i] = __ldg(llr + q + N / 2);
+        }
+        for (int i = tid; i < (n - 1) * N; i += THREADS) Lm[i] = (real)0;  // BP_1024.c:378-380
+        if (tid < W + 1) uh[tid] = 0;
+        cta_sync<THREADS>();
+
+        int sweeps = 0;
+        for (int it = 0; it < a.iters; it++) {
+            // ---- R pass, stages 0..n-2 (stage n-1 would only produce r(n), which nothing reads)
+            for (int s = 0; s < n - 1; s++) {
+                const int d = 1 << s;
+                const real *rin = Rm + (size_t)(s - 1) * N;
+                const real *lin = Lm + (size_t)s * N;       // l(s+1,.)
+                real *rout = Rm + (size_t)s * N;            // r(s+1,.)
+#pragma unroll
+                for (int i = 0; i < BPT; i++) {
+                    const int q = tid + i * THREADS;
+                    const int j = ((q >> s) << (s + 1)) | (q & (d - 1));
+                    const real ru = (s == 0) ? r0(j) : rin[j];
+                    const real rl = (s == 0) ? r0(j + d) : rin[j + d];
+                    const real lu = lin[j], ll = lin[j + d];
+                    rout[j] = chk<real>(ru, ll + rl);
+                    rout[j + d] = rl + chk<real>(ru, lu);
+                }
+                cta_sync<THREADS>();
+            }
+            // ---- L pass, stages n-1..1
+            int changed = 0;
+            for (int s = n - 1; s >= 1; s--) {
+                const int d = 1 << s;
+                const real *rin = Rm + (size_t)(s - 1) * N;  // r(s,.)
+                const real *lin = Lm + (size_t)s * N;        // l(s+1,.) (unused for s = n-1)
+                real *lout = Lm + (size_t)(s - 1) * N;       // l(s,.)
+#pragma unroll
+                for (int i = 0; i < BPT; i++) {
+                    const int q = tid + i * THREADS;
+                    const int j = ((q >> s) << (s + 1)) | (q & (d - 1));
+                    const real lu = (s == n - 1) ? ch_up[i] : lin[j];
+                    const real ll = (s == n - 1) ? ch_lo[i] : lin[j + d];
+                    const real ru = rin[j], rl = rin[j + d];
+                    const real ou = chk<real>(lu, ll + rl);
+                    const real ol = ll + chk<real>(ru, lu);
+                    if (a.early_stop) changed |= (int)(!RT::same_bits(ou, lout[j])) | (int)(!RT::same_bits(ol, lout[j + d]));
+                    lout[j] = ou;
+                    lout[j + d] = ol;
+                }
+                cta_sync<THREADS>();
+            }
+            sweeps = it + 1;
+            if (a.early_stop) {
+                const int any = (THREADS == 32) ? __any_sync(0xffffffffu, changed) : __syncthreads_or(changed);
+                if (!any) break;
+            }
+        }
+        // ---- l(0,.) from the final state and the decision (BP_1024.c:410-413,417-425)
+        {
+            const real *lin = Lm;  // l(1,.)
+#pragma unroll
+            for (int i = 0; i < BPT; i++) {
+                const int q = tid + i * THREADS;
+                const int j = 2 * q;
+                const real lu = (n == 1) ? ch_up[i] : lin[j];
+                const real ll = (n == 1) ? ch_lo[i] : lin[j + 1];
+                const real ru = r0(j), rl = r0(j + 1);
+                const real ou = chk<real>(lu, ll + rl);
+                const real ol = ll + chk<real>(ru, lu);
+                const uint32_t iu = (a.m.info[j >> 5] >> (j & 31)) & 1u, il = (a.m.info[j >> 5] >> ((j & 31) + 1)) & 1u;
+                const uint32_t bu = (iu && !(ou + ru >= (real)0)) ? 1u : 0u;
+                const uint32_t bl = (il && !(ol + rl >= (real)0)) ? 1u : 0u;
+                const uint32_t two = bu | (bl << 1);
+                if (two) atomicOr(&uh[j >> 5], two << (j & 31));
+            }
+        }
+        cta_sync<THREADS>();
+        if (tid < W) {
+            const uint32_t w = uh[tid];
+            if (a.u_hat) a.u_hat[frame * (size_t)W + tid] = w;
+            if (a.truth) {
+                const uint32_t e = __popc((w ^ __ldg(a.truth + frame * (size_t)W + tid)) & a.m.cnt[tid]);
+                if (e) atomicAdd(&uh[W], e);
+            }
+        }
+        cta_sync<THREADS>();
+        if (tid == 0) {
+            const uint32_t nerr = uh[W];
+            if (a.frame_info) a.frame_info[frame] = (nerr > 0xFFFFu ? 0xFFFFu : nerr) | ((uint32_t)(sweeps > 255 ? 255 : sweeps) << 24);
+            if (a.counters) {
+                atomicAdd(a.counters + CNT_FRAMES, 1ull);
+                if (nerr) { atomicAdd(a.counters + CNT_ERR_BLOCKS, 1ull); atomicAdd(a.counters + CNT_ERR_BITS, (unsigned long long)nerr); }
+                atomicAdd(a.counters + CNT_SWEEPS, (unsigned long long)sweeps);
+            }
+        }
+        cta_sync<THREADS>();
+    }
+}
+
+template <typename real, int LOGN, int THREADS>
+struct BpDispatch {
+    using C = BpCfg<real, LOGN, THREADS>;
+    static cudaError_t plan(BpPlan *p)
+    {
+        auto kern = bp_decode_kernel<real, LOGN, THREADS>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        if (e != cudaSuccess) return e;
+        int nb = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, THREADS, C::SMEM);
+        if (e != cudaSuccess) return e;
+        p->smem = C::SMEM;
+        p->ctas_per_sm = nb;
+        p->threads = THREADS;
+        return cudaSuccess;
+    }
+    static cudaError_t launch(const BpArgs &a, int grid, cudaStream_t st)
+    {
+        bp_decode_kernel<real, LOGN, THREADS><<<grid, THREADS, C::SMEM, st>>>(a);
+        return cudaGetLastError();
+    }
+};
+
+// threads per frame: fp32 N/4 (two butterflies per thread), fp64 N/2 for N=1024 (one frame per SM: use more threads)
+#define POLAR_BP_CASES(X) X(6, 32, 32) X(7, 32, 32) X(8, 64, 64) X(9, 128, 128) X(10, 256, 512)
+
+cudaError_t bp_plan(int n, bool f64, BpPlan *plan)
+{
+#define X(NN, T32, T64) \
+    if (n == NN) return f64 ? BpDispatch<double, NN, T64>::plan(plan) : BpDispatch<float, NN, T32>::plan(plan);
+    POLAR_BP_CASES(X)
+#undef X
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_bp(const BpArgs &a, int n, bool f64, int grid, cudaStream_t st)
+{
+#define X(NN, T32, T64) \
+    if (n == NN) return f64 ? BpDispatch<double, NN, T64>::launch(a, grid, st) : BpDispatch<float, NN, T32>::launch(a, grid, st);
+    POLAR_BP_CASES(X)
+#undef X
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace polar

@@ -1,0 +1,457 @@
+// SC / SC-List / CRC-aided SC-List decoding, one PATH per lane (sm_100a).
+//
+// What it computes (reference): SCdecode /root/reference/SC_128.c:395-460, SCLdecode
+// /root/reference/SCL_1024.c:547-680, CASCL /root/reference/CASCL_1024_L8.c:601-761, with
+// CHK (SC_128.c:284-315), the g function (SC_128.c:355-359), PHI (SCL_1024.c:481-502), the
+// "< med" survivor rule and slot re-use order (SCL_1024.c:619-661) and CRcheck
+// (CASCL_1024_L8.c:569-598).  How: nothing like the reference's pointer graph.
+//
+//  * A warp decodes 32/L frames side by side; lane = (frame, path slot k).  All lanes run the SAME
+//    instruction stream (the SC schedule does not depend on data), so there is no divergence, and
+//    every f/g evaluation of a path is lane-private: no barrier inside a path, ILP from the 4-wide
+//    unrolled layers.  Paths that do not exist yet (list filling) carry PM=+inf and read path 0's data.
+//  * Array formulation: at bit j, t=ctz(j): one g-layer at stage t then f-layers t-1..0; stage s keeps
+//    2^s live LLRs.  Stages 0..2 live in registers (a fully unrolled 4-leaf subtree), stages
+//    3..SMEM_TOP-1 in shared memory, the rest in an L2-resident global scratch, all laid out
+//    [idx/4][lane][4] so that a warp's 128-bit accesses are contiguous/conflict-free.
+//  * Lazy copy: every path owns a HOME array per stage and a packed pointer word saying where its
+//    current stage-s data lives.  Stage s is rewritten by all paths at the same bits (multiples of
+//    2^s), always into the home array, so a clone is a register shuffle of the pointer word -- the
+//    reference copies the whole graph instead (copyPath/simpleCopy, 74 % of its run time).
+//  * Partial sums are kept as packed bit vectors per stage (B[s], 2^s bits) with the same pointer
+//    scheme; stages 2..5 are registers.  The final B[n] is the re-encoded codeword, u_hat = B[n] F^{(x)n}.
+//  * List pruning: each lane ranks its two candidates against the 2L candidates of its frame with
+//    shuffles.  If all candidates are distinct (checked with one warp reduction) rank < L is exactly
+//    the reference's "PM < med"; otherwise (exact ties, or +inf dummies while the list fills) a slow
+//    path applies the total order (value, candidate index) and flags frames where the reference's
+//    rule would have been ambiguous ("Oops!", SCL_1024.c:621).
+#include "engine.h"
+#include "polar_common.cuh"
+
+namespace polar {
+
+template <typename real> struct alignas(16) vec4 { real v[4]; };
+
+template <int L> struct ptr_word { using type = uint32_t; static constexpr int W = 4; };
+template <> struct ptr_word<32> { using type = unsigned long long; static constexpr int W = 5; };
+
+template <typename T>
+__device__ __forceinline__ T shfl_any(T v, int src)
+{
+    return __shfl_sync(0xffffffffu, v, src);
+}
+
+template <typename real, int LOGN, int L, int SMEM_TOP>
+struct ListCfg {
+    static constexpr int N = 1 << LOGN;
+    static constexpr int W = (N + 31) / 32;
+    static constexpr int FPW = 32 / L;
+    static constexpr int TOP = (SMEM_TOP < LOGN) ? SMEM_TOP : LOGN;  // stages 3..TOP-1 in smem
+    // reals of shared memory for the stage arrays, words for the bit arrays (stages 6..LOGN)
+    static constexpr int SM_STAGE_REALS = 32 * ((1 << TOP) - 8);
+    static constexpr int SM_BIT_WORDS = (LOGN >= 6) ? 32 * ((1 << (LOGN - 4)) - 2) : 0;
+    static constexpr size_t SMEM = (size_t)SM_STAGE_REALS * sizeof(real) + (size_t)SM_BIT_WORDS * 4;
+    static constexpr size_t GS_REALS = 32 * (size_t)((1 << LOGN) - (1 << TOP));  // stages TOP..LOGN-1
+};
+
+template <typename real, int LOGN, int L, int SMEM_TOP>
+__global__ void __launch_bounds__(32) list_decode_kernel(const ListArgs a)
+{
+    using C = ListCfg<real, LOGN, L, SMEM_TOP>;
+    using RT = real_traits<real>;
+    using PW = ptr_word<L>;
+    using ptr_t = typename PW::type;
+    constexpr int N = C::N, W = C::W, FPW = C::FPW, TOP = C::TOP;
+    constexpr int PWID = PW::W;
+    constexpr ptr_t PMASK = (ptr_t)((1u << PWID) - 1);
+    constexpr uint32_t LMASK = (L == 32) ? 0xffffffffu : ((1u << (L & 31)) - 1u);  // lanes of one frame
+    const real INF = RT::inf();
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    real *sm_stage = reinterpret_cast<real *>(smem_raw);
+    uint32_t *sm_bits = reinterpret_cast<uint32_t *>(smem_raw + (size_t)C::SM_STAGE_REALS * sizeof(real));
+    real *gs_stage = reinterpret_cast<real *>(a.gscratch) + (size_t)blockIdx.x * C::GS_REALS;
+
+    const int lane = threadIdx.x;
+    const int k = lane & (L - 1);
+    const int fbase = lane - k;
+    const int fl = lane / L;
+    const unsigned long long groups = (a.B + FPW - 1) / FPW;
+
+    // stage s array (s>=3), as vec4 groups: element group i4 of physical lane pl is [i4*32 + pl]
+    auto stage4 = [&](int s) -> vec4<real> * {
+        real *base = (s < TOP) ? (sm_stage + 32 * ((1 << s) - 8)) : (gs_stage + 32 * (size_t)((1 << s) - (1 << TOP)));
+        return reinterpret_cast<vec4<real> *>(base);
+    };
+    // bit array of stage s (s>=6): word w of physical lane pl is [w*32 + pl]
+    auto bits_of = [&](int s) -> uint32_t * { return sm_bits + 32 * ((1 << (s - 5)) - 2); };
+
+    for (unsigned long long g = blockIdx.x; g < groups; g += gridDim.x) {
+        unsigned long long frame = g * FPW + fl;
+        const bool valid = frame < a.B;
+        if (!valid) frame = a.B - 1;  // tail lanes decode a duplicate and write nothing
+        const vec4<real> *ch4 = reinterpret_cast<const vec4<real> *>(reinterpret_cast<const real *>(a.llr) + frame * (size_t)N);
+
+        real s2[4] = {0, 0, 0, 0}, s1[2] = {0, 0}, pm;
+        ptr_t ptr = 0, bptr = 0;  // fields: stage s at (s-3)*PWID / bit stage s at (s-6)*PWID
+        uint32_t Blow = 0, B5 = 0, ug = 0, flags = 0;
+        pm = (k == 0) ? (real)0 : INF;
+        if (L == 1) pm = (real)0;
+
+        auto pfield = [&](int s) -> int { return (L == 1) ? 0 : (int)((ptr >> ((s - 3) * PWID)) & PMASK); };
+        auto bfield = [&](int s) -> int { return (L == 1) ? 0 : (int)((bptr >> ((s - 6) * PWID)) & PMASK); };
+        auto set_pfield = [&](int s, int v) {
+            if (L > 1) ptr = (ptr & ~(PMASK << ((s - 3) * PWID))) | ((ptr_t)v << ((s - 3) * PWID));
+        };
+        auto set_bfield = [&](int s, int v) {
+            if (L > 1) bptr = (bptr & ~(PMASK << ((s - 6) * PWID))) | ((ptr_t)v << ((s - 6) * PWID));
+        };
+
+
+        // ---- f-layer producing stage s (3 <= s < LOGN) from stage s+1 ------------------------------------
+        auto f_layer = [&](int s) {
+            const bool alive = pm < INF;
+            const int cnt4 = 1 << (s - 2);
+            vec4<real> *dst = stage4(s) + lane;
+            if (s + 1 == LOGN) {
+#pragma unroll 2
+                for (int i4 = 0; i4 < cnt4; i4++) {
+                    const vec4<real> x = ch4[i4], y = ch4[i4 + cnt4];
+                    vec4<real> o;
+#pragma unroll
+                    for (int e = 0; e < 4; e++) o.v[e] = chk<real>(x.v[e], y.v[e]);
+                    if (alive) dst[i4 * 32] = o;
+                }
+            } else {
+                const vec4<real> *src = stage4(s + 1) + fbase + pfield(s + 1);
+#pragma unroll 2
+                for (int i4 = 0; i4 < cnt4; i4++) {
+                    const vec4<real> x = src[i4 * 32], y = src[(i4 + cnt4) * 32];
+                    vec4<real> o;
+#pragma unroll
+                    for (int e = 0; e < 4; e++) o.v[e] = chk<real>(x.v[e], y.v[e]);
+                    if (alive) dst[i4 * 32] = o;
+                }
+            }
+            set_pfield(s, alive ? k : 0);
+            __syncwarp();
+        };
+
+        // partial-sum bits of stage t for nodes 4*i4 .. 4*i4+3 (t >= 2)
+        auto bits4 = [&](int t, int i4) -> uint32_t {
+            if (t == 2) return Blow & 0xF;
+            if (t == 3) return (Blow >> (4 + 4 * i4)) & 0xF;
+            if (t == 4) return (Blow >> (12 + 4 * i4)) & 0xF;
+            if (t == 5) return (B5 >> (4 * i4)) & 0xF;
+            const uint32_t w = bits_of(t)[(i4 >> 3) * 32 + fbase + bfield(t)];
+            return (w >> ((i4 & 7) * 4)) & 0xF;
+        };
+
+        // ---- g-layer producing stage t (3 <= t < LOGN) from stage t+1 and B[t] ---------------------------
+        auto g_layer = [&](int t) {
+            const bool alive = pm < INF;
+            const int cnt4 = 1 << (t - 2);
+            vec4<real> *dst = stage4(t) + lane;
+            const bool from_ch = (t + 1 == LOGN);
+            const vec4<real> *src = from_ch ? ch4 : (stage4(t + 1) + fbase + pfield(t + 1));
+            const int stride = from_ch ? 1 : 32;
+#pragma unroll 2
+            for (int i4 = 0; i4 < cnt4; i4++) {
+                const vec4<real> up = src[i4 * stride], lo = src[(i4 + cnt4) * stride];
+                const uint32_t b = bits4(t, i4);
+                vec4<real> o;
+#pragma unroll
+                for (int e = 0; e < 4; e++) o.v[e] = lo.v[e] + RT::flip(up.v[e], (b >> e) & 1u);
+                if (alive) dst[i4 * 32] = o;
+            }
+            set_pfield(t, alive ? k : 0);
+            __syncwarp();
+        };
+
+        // stage 3 -> registers (stage 2)
+        auto stage2_from3 = [&](bool is_g) {
+            const vec4<real> *src = stage4(3) + fbase + pfield(3);
+            const vec4<real> up = src[0], lo = src[32];
+            if (is_g) {
+                const uint32_t b = Blow & 0xF;
+#pragma unroll
+                for (int e = 0; e < 4; e++) s2[e] = lo.v[e] + RT::flip(up.v[e], (b >> e) & 1u);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; e++) s2[e] = chk<real>(up.v[e], lo.v[e]);
+            }
+        };
+
+        // ---- one leaf: frozen -> PM only; information -> decide (SC) or fork/prune (list) ------------------
+        auto leaf = [&](int j, real lam) -> uint32_t {
+            const bool info = (a.m.info[j >> 5] >> (j & 31)) & 1u;
+            if (L == 1) return (info && !(lam >= (real)0)) ? 1u : 0u;  // SC_128.c:426-431
+            const real ab = rabs(lam);
+            const real t = tbl8<real>(ab);
+            real pen = t;
+            pen += ab;  // PHI: result = table; result += |l| on a mismatch (SCL_1024.c:489-500)
+            if (!info) {
+                pm = pm + ((lam < (real)0) ? pen : t);
+                return 0u;
+            }
+            const real c0 = pm + ((lam < (real)0) ? pen : t);
+            const real c1 = pm + ((lam > (real)0) ? pen : t);
+            int n0 = 0, n1 = 0;
+#pragma unroll
+            for (int i = 0; i < L; i++) {
+                const real v0 = __shfl_sync(0xffffffffu, c0, i, L);
+                const real v1 = __shfl_sync(0xffffffffu, c1, i, L);
+                n0 += (int)(v0 < c0) + (int)(v1 < c0);
+                n1 += (int)(v0 < c1) + (int)(v1 < c1);
+            }
+            bool k0, k1;  // candidate survives
+            const int tot = __reduce_add_sync(0xffffffffu, n0 + n1);
+            if (tot == 32 * (2 * L - 1)) {  // all 2L candidates of every frame distinct and finite
+                k0 = n0 < L;
+                k1 = n1 < L;
+            } else {
+                const bool f0 = c0 < INF, f1 = c1 < INF;
+                const real d0 = f0 ? c0 : INF, d1 = f1 ? c1 : INF;
+                int r0 = 0, r1 = 0, le0 = 0, le1 = 0;
+#pragma unroll
+                for (int i = 0; i < L; i++) {
+                    const real v0 = __shfl_sync(0xffffffffu, d0, i, L);
+                    const real v1 = __shfl_sync(0xffffffffu, d1, i, L);
+                    // candidate order of the reference's PMcand array: bit-0 branch of path i at i, bit-1 branch at i+L
+                    r0 += (int)((v0 < d0) || (v0 == d0 && i < k)) + (int)(v1 < d0);
+                    r1 += (int)(v0 <= d1) + (int)((v1 < d1) || (v1 == d1 && i < k));
+                    le0 += (int)(v0 <= d0) + (int)(v1 <= d0);
+                    le1 += (int)(v0 <= d1) + (int)(v1 <= d1);
+                }
+                k0 = f0 && r0 < L;
+                k1 = f1 && r1 < L;
+                const bool q0 = f0 && le0 <= L, q1 = f1 && le1 <= L;  // the reference's "PM < med"
+                const uint32_t amb = __ballot_sync(0xffffffffu, (q0 != k0) || (q1 != k1));
+                if (amb & (LMASK << fbase)) flags |= kInfoTie;
+            }
+            const uint32_t m0 = __ballot_sync(0xffffffffu, k0), m1 = __ballot_sync(0xffffffffu, k1);
+            const uint32_t fmask = LMASK << fbase;
+            const uint32_t both = m0 & m1 & fmask, dead = ~(m0 | m1) & fmask;
+            int src = lane;
+            if (!(k0 || k1)) {
+                // t-th free slot (ascending) takes the bit-1 branch of the t-th both-survivor (ascending): SCL_1024.c:636-660
+                const int td = __popc(dead & ((1u << lane) - 1u));
+                if (td < __popc(both)) src = (int)__fns(both, 0, td + 1);
+            }
+            const real pc1 = __shfl_sync(0xffffffffu, c1, src);
+#pragma unroll
+            for (int e = 0; e < 4; e++) s2[e] = __shfl_sync(0xffffffffu, s2[e], src);
+            s1[0] = __shfl_sync(0xffffffffu, s1[0], src);
+            s1[1] = __shfl_sync(0xffffffffu, s1[1], src);
+            ptr = shfl_any(ptr, src);
+            bptr = shfl_any(bptr, src);
+            Blow = __shfl_sync(0xffffffffu, Blow, src);
+            B5 = __shfl_sync(0xffffffffu, B5, src);
+            ug = __shfl_sync(0xffffffffu, ug, src);
+            uint32_t u;
+            if (src != lane) { pm = pc1; u = 1u; }
+            else if (k0) { pm = c0; u = 0u; }
+            else if (k1) { pm = c1; u = 1u; }
+            else { pm = INF; u = 0u; }
+            return u;
+        };
+
+        // =================================================================== the N/4 leaf groups
+        for (int j4 = 0; j4 < N / 4; j4++) {
+            if (j4 == 0) {
+                for (int s = LOGN - 1; s >= 3; s--) f_layer(s);
+                stage2_from3(false);
+            } else {
+                const int t = __ffs(j4) - 1 + 2;
+                if (t == 2) {
+                    stage2_from3(true);
+                } else {
+                    g_layer(t);
+                    for (int s = t - 1; s >= 3; s--) f_layer(s);
+                    stage2_from3(false);
+                }
+            }
+            const int j = 4 * j4;
+            ug = 0;
+            // leaf 0: f at stages 1, 0
+            s1[0] = chk<real>(s2[0], s2[2]);
+            s1[1] = chk<real>(s2[1], s2[3]);
+            uint32_t u = leaf(j, chk<real>(s1[0], s1[1]));
+            ug |= u;
+            // leaf 1: g at stage 0
+            u = leaf(j + 1, s1[1] + RT::flip(s1[0], ug & 1u));
+            ug |= u << 1;
+            // leaf 2: g at stage 1 (partial sums u0^u1, u1), f at stage 0
+            s1[0] = s2[2] + RT::flip(s2[0], (ug ^ (ug >> 1)) & 1u);
+            s1[1] = s2[3] + RT::flip(s2[1], (ug >> 1) & 1u);
+            u = leaf(j + 2, chk<real>(s1[0], s1[1]));
+            ug |= u << 2;
+            // leaf 3: g at stage 0
+            u = leaf(j + 3, s1[1] + RT::flip(s1[0], (ug >> 2) & 1u));
+            ug |= u << 3;
+
+            // ---- partial sums of the finished 4-block, pushed up while the block closes larger blocks -------
+            const uint32_t u0 = ug & 1u, u1 = (ug >> 1) & 1u, u2b = (ug >> 2) & 1u, u3 = (ug >> 3) & 1u;
+            uint32_t t32 = (u0 ^ u1 ^ u2b ^ u3) | ((u1 ^ u3) << 1) | ((u2b ^ u3) << 2) | (u3 << 3);
+            const int z = __ffs(~j4) - 1;  // trailing ones of j4
+            int T = 2 + z;
+            if (T > LOGN) T = LOGN;
+            if (T > 2) t32 = ((Blow & 0xF) ^ t32) | (t32 << 4);
+            if (T > 3) t32 = (((Blow >> 4) & 0xFF) ^ t32) | (t32 << 8);
+            if (T > 4) t32 = (((Blow >> 12) & 0xFFFF) ^ t32) | (t32 << 16);
+            if (T == 2) Blow = (Blow & ~0xFu) | t32;
+            else if (T == 3) Blow = (Blow & ~0xFF0u) | (t32 << 4);
+            else if (T == 4) Blow = (Blow & ~0xFFFF000u) | (t32 << 12);
+            else if (T == 5) B5 = t32;
+            else {
+                const bool alive = pm < INF;
+                uint32_t *dst = bits_of(T) + lane;
+                const uint32_t w0 = B5 ^ t32;
+                if (alive) { dst[0] = w0; dst[32] = t32; }
+                for (int s = 6; s < T; s++) {
+                    const int len = 1 << (s - 5);
+                    const uint32_t *srcb = bits_of(s) + fbase + bfield(s);
+                    for (int i = 0; i < len; i++) {
+                        const uint32_t d = dst[i * 32];
+                        if (alive) { dst[(i + len) * 32] = d; dst[i * 32] = d ^ srcb[i * 32]; }
+                    }
+                }
+                set_bfield(T, alive ? k : 0);
+                __syncwarp();
+            }
+        }
+
+        // =================================================================== termination
+        // x_hat = B[LOGN] of this path; u_hat = x_hat F^{(x)n}
+        uint32_t xw[W];
+        if (LOGN == 5) {
+            xw[0] = B5;
+        } else {
+            const uint32_t *srcb = bits_of(LOGN) + fbase + bfield(LOGN);
+#pragma unroll
+            for (int w = 0; w < W; w++) xw[w] = srcb[w * 32];
+        }
+#pragma unroll
+        for (int w = 0; w < W; w++) xw[w] = polar_word_stages(xw[w]);
+#pragma unroll
+        for (int d = 1; d < W; d <<= 1)
+#pragma unroll
+            for (int w = 0; w < W; w++)
+                if (!(w & d)) xw[w] ^= xw[w + d];
+
+        int best = 0;
+        if (L > 1) {
+            bool pass = false;
+            if (a.use_crc) {  // CRcheck: remainder of the I[]-ordered word modulo g(D), as r parity masks
+                uint32_t syn = 0;
+                for (int b = 0; b < a.r; b++) {
+                    uint32_t acc = 0;
+#pragma unroll
+                    for (int w = 0; w < W; w++) acc ^= xw[w] & __ldg(a.crc_masks + b * W + w);
+                    syn |= (uint32_t)(__popc(acc) & 1);
+                }
+                pass = (syn == 0) && (pm < INF);
+            }
+            // CASCL_1024_L8.c:725-755 / SCL_1024.c:667-674: first index wins ties
+            int bi = -1;
+            real bpm = INF;
+#pragma unroll
+            for (int i = 0; i < L; i++) {
+                const real v = __shfl_sync(0xffffffffu, pm, i, L);
+                const bool ps = __shfl_sync(0xffffffffu, (int)pass, i, L) != 0;
+                if (ps && (bi < 0 || v < bpm)) { bi = i; bpm = v; }
+            }
+            if (bi < 0) {
+                if (a.use_crc) flags |= kInfoCrcFail;
+                bi = 0;
+                bpm = __shfl_sync(0xffffffffu, pm, 0, L);
+#pragma unroll
+                for (int i = 1; i < L; i++) {
+                    const real v = __shfl_sync(0xffffffffu, pm, i, L);
+                    if (v < bpm) { bi = i; bpm = v; }
+                }
+            }
+            best = bi;
+        }
+        uint32_t fr_flags = flags;
+        if (L > 1) {  // OR over the frame's lanes
+#pragma unroll
+            for (int d = 1; d < L; d <<= 1) fr_flags |= __shfl_xor_sync(0xffffffffu, fr_flags, d);
+        }
+        if (valid && k == best) {
+            uint32_t nerr = 0;
+            if (a.truth) {
+                const uint32_t *tw = a.truth + frame * (size_t)W;
+#pragma unroll
+                for (int w = 0; w < W; w++) nerr += __popc((xw[w] ^ __ldg(tw + w)) & a.m.cnt[w]);
+            }
+            if (a.u_hat) {
+                uint32_t *ow = a.u_hat + frame * (size_t)W;
+#pragma unroll
+                for (int w = 0; w < W; w++) ow[w] = xw[w] & a.m.info[w];
+            }
+            if (a.frame_info) a.frame_info[frame] = (nerr > 0xFFFFu ? 0xFFFFu : nerr) | fr_flags;
+            if (a.counters) {
+                atomicAdd(a.counters + CNT_FRAMES, 1ull);
+                if (nerr) { atomicAdd(a.counters + CNT_ERR_BLOCKS, 1ull); atomicAdd(a.counters + CNT_ERR_BITS, (unsigned long long)nerr); }
+                if (fr_flags & kInfoTie) atomicAdd(a.counters + CNT_TIE, 1ull);
+                if (fr_flags & kInfoCrcFail) atomicAdd(a.counters + CNT_CRCFAIL, 1ull);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------- dispatch
+template <typename real, int LOGN, int L>
+struct ListDispatch {
+    static constexpr int SMEM_TOP = 7;
+    using C = ListCfg<real, LOGN, L, SMEM_TOP>;
+    static cudaError_t plan(ListPlan *p)
+    {
+        auto kern = list_decode_kernel<real, LOGN, L, SMEM_TOP>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        if (e != cudaSuccess) return e;
+        int nb = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 32, C::SMEM);
+        if (e != cudaSuccess) return e;
+        p->scratch_per_cta = C::GS_REALS * sizeof(real);
+        p->smem = C::SMEM;
+        p->ctas_per_sm = nb;
+        p->frames_per_cta = C::FPW;
+        return cudaSuccess;
+    }
+    static cudaError_t launch(const ListArgs &a, int grid, cudaStream_t st)
+    {
+        list_decode_kernel<real, LOGN, L, SMEM_TOP><<<grid, 32, C::SMEM, st>>>(a);
+        return cudaGetLastError();
+    }
+};
+
+#define POLAR_LIST_CASES(X) \
+    X(5, 1) X(5, 2) X(5, 4) X(5, 8) \
+    X(6, 1) X(6, 2) X(6, 4) X(6, 8) \
+    X(7, 1) X(7, 2) X(7, 4) X(7, 8) X(7, 16) X(7, 32) \
+    X(8, 1) X(8, 2) X(8, 4) X(8, 8) X(8, 16) X(8, 32) \
+    X(9, 1) X(9, 2) X(9, 4) X(9, 8) X(9, 16) X(9, 32) \
+    X(10, 1) X(10, 2) X(10, 4) X(10, 8) X(10, 16) X(10, 32)
+
+cudaError_t list_plan(int n, int L, bool f64, ListPlan *plan)
+{
+#define X(NN, LL) \
+    if (n == NN && L == LL) return f64 ? ListDispatch<double, NN, LL>::plan(plan) : ListDispatch<float, NN, LL>::plan(plan);
+    POLAR_LIST_CASES(X)
+#undef X
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_list(const ListArgs &a, int n, int L, bool f64, int grid, cudaStream_t st)
+{
+#define X(NN, LL) \
+    if (n == NN && L == LL) return f64 ? ListDispatch<double, NN, LL>::launch(a, grid, st) : ListDispatch<float, NN, LL>::launch(a, grid, st);
+    POLAR_LIST_CASES(X)
+#undef X
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace polar

@@ -1,0 +1,103 @@
+// Device-side primitives shared by every kernel of the polar decoding engine (sm_100a).
+//
+// Arithmetic contract (parity): every floating-point operation below is an IEEE add, subtract,
+// compare, min or sign manipulation performed in the SAME order as the reference C code, so the
+// `double` instantiation reproduces the reference's fp64 results bit for bit; the `float`
+// instantiation is the throughput mode (same formulas, fp32 rounding).
+//   chk<real>  : CHK(),  /root/reference/SC_128.c:284-315
+//   phi_tbl    : table part of PHI(), /root/reference/SCL_1024.c:481-502 (same 8-level table)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace polar {
+
+template <typename real> struct real_traits;
+template <> struct real_traits<float> {
+    static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
+    static __device__ __forceinline__ float flip(float v, uint32_t bit) {  // bit ? -v : v
+        return __int_as_float(__float_as_int(v) ^ (int)(bit << 31));
+    }
+    static __device__ __forceinline__ float xsign(float m, float a, float b) {  // m with sign(a)*sign(b) applied
+        return __int_as_float(__float_as_int(m) ^ ((__float_as_int(a) ^ __float_as_int(b)) & 0x80000000));
+    }
+    static __device__ __forceinline__ bool same_bits(float a, float b) { return __float_as_int(a) == __float_as_int(b); }
+};
+template <> struct real_traits<double> {
+    static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000ll); }
+    static __device__ __forceinline__ double flip(double v, uint32_t bit) {
+        return __hiloint2double(__double2hiint(v) ^ (int)(bit << 31), __double2loint(v));
+    }
+    static __device__ __forceinline__ double xsign(double m, double a, double b) {
+        return __hiloint2double(__double2hiint(m) ^ ((__double2hiint(a) ^ __double2hiint(b)) & 0x80000000), __double2loint(m));
+    }
+    static __device__ __forceinline__ bool same_bits(double a, double b) {
+        return __double_as_longlong(a) == __double_as_longlong(b);
+    }
+};
+
+__device__ __forceinline__ float rabs(float v) { return fabsf(v); }
+__device__ __forceinline__ double rabs(double v) { return fabs(v); }
+__device__ __forceinline__ float rmin(float a, float b) { return fminf(a, b); }
+__device__ __forceinline__ double rmin(double a, double b) { return fmin(a, b); }
+
+// 8-level table for ln(1+e^-x), x >= 0 (SC_128.c:293-300)
+template <typename real>
+__device__ __forceinline__ real tbl8(real a)
+{
+    real t = (real)0;
+    t = (a < (real)4.5) ? (real)0.05 : t;
+    t = (a < (real)2.252) ? (real)0.15 : t;
+    t = (a < (real)1.508) ? (real)0.25 : t;
+    t = (a < (real)1.05) ? (real)0.35 : t;
+    t = (a < (real)0.71) ? (real)0.45 : t;
+    t = (a < (real)0.433) ? (real)0.55 : t;
+    t = (a < (real)0.196) ? (real)0.65 : t;
+    return t;
+}
+
+// CHK(a,b) = sign(a)sign(b) min(|a|,|b|) + (T(|a+b|) - T(|a-b|)).
+// The reference multiplies the int sign product into the double magnitude (exact) and uses sign(0)=+1;
+// a sign-bit XOR differs only for a -0.0 operand, where the magnitude is 0 and (+-0) + delta is the
+// same value for every delta the table difference can produce (delta is never -0.0).
+template <typename real>
+__device__ __forceinline__ real chk(real a, real b)
+{
+    const real sa = rabs(a + b);
+    const real da = rabs(a - b);
+    const real delta = tbl8<real>(sa) - tbl8<real>(da);
+    const real m = rmin(rabs(a), rabs(b));
+    return real_traits<real>::xsign(m, a, b) + delta;
+}
+
+// ---------------------------------------------------------------- Philox4x32-10 (counter based)
+struct philox4 { uint32_t x, y, z, w; };
+
+__device__ __forceinline__ philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
+{
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+        const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += W0; k1 += W1;
+    }
+    philox4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3;
+    return o;
+}
+
+// ---------------------------------------------------------------- packed-bit polar transform
+// In-register butterfly stages 0..4 of x = u F^{(x)n} on one 32-bit word (bit p of the word = position p).
+__device__ __forceinline__ uint32_t polar_word_stages(uint32_t w)
+{
+    w ^= (w >> 1) & 0x55555555u;
+    w ^= (w >> 2) & 0x33333333u;
+    w ^= (w >> 4) & 0x0F0F0F0Fu;
+    w ^= (w >> 8) & 0x00FF00FFu;
+    w ^= (w >> 16) & 0x0000FFFFu;
+    return w;
+}
+
+}  // namespace polar
