@@ -299,6 +299,16 @@ extern "C" int pg_info_set(const pg_ctx *ctx, int *I_out, uint8_t *inI_out)
 }
 
 // ---------------------------------------------------------------- launches
+// POLARGPU_DEBUG=1: synchronise after every kernel so that a fault is attributed to the launch that caused it
+static int debug_sync(pg_ctx *ctx, const char *what)
+{
+    static const bool on = getenv("POLARGPU_DEBUG") != nullptr;
+    if (!on) return PG_OK;
+    cudaError_t e = cudaStreamSynchronize(ctx->st);
+    if (e != cudaSuccess) { ctx->err = std::string(what) + " kernel: " + cudaGetErrorString(e); return PG_ERR_CUDA; }
+    return PG_OK;
+}
+
 static int run_channel(pg_ctx *ctx, double ebn0_db, uint64_t first, size_t B, bool want_llr)
 {
     ChannelArgs a;
@@ -318,7 +328,7 @@ static int run_channel(pg_ctx *ctx, double ebn0_db, uint64_t first, size_t B, bo
     CU(cudaEventRecord(ctx->ev[1], ctx->st));
     ctx->ev_ch = true;
     ctx->launches++;
-    return PG_OK;
+    return debug_sync(ctx, "channel");
 }
 
 static int run_decode(pg_ctx *ctx, const void *d_llr, size_t B, const uint32_t *d_truth, uint32_t *d_uhat, uint32_t *d_info, bool count)
@@ -356,7 +366,7 @@ static int run_decode(pg_ctx *ctx, const void *d_llr, size_t B, const uint32_t *
     CU(cudaEventRecord(ctx->ev[3], ctx->st));
     ctx->ev_dec = true;
     ctx->launches++;
-    return PG_OK;
+    return debug_sync(ctx, "decode");
 }
 
 extern "C" int pg_decode_llr_device(pg_ctx *ctx, const void *d_llr, int llr_is_f64, size_t B, uint32_t *d_u_hat_packed, uint32_t *d_flags)

@@ -352,24 +352,20 @@ __global__ void __launch_bounds__(32) list_decode_kernel(const ListArgs a)
                 }
                 pass = (syn == 0) && (pm < INF);
             }
-            // CASCL_1024_L8.c:725-755 / SCL_1024.c:667-674: first index wins ties
-            int bi = -1;
-            real bpm = INF;
+            // CASCL_1024_L8.c:725-755 / SCL_1024.c:667-674: first index wins ties.  Both scans run on every lane
+            // (frames of one warp may disagree on whether a CRC-passing path exists; shuffles must stay convergent).
+            int bi = -1, mi = 0;
+            real bpm = INF, mpm = __shfl_sync(0xffffffffu, pm, 0, L);
 #pragma unroll
             for (int i = 0; i < L; i++) {
                 const real v = __shfl_sync(0xffffffffu, pm, i, L);
                 const bool ps = __shfl_sync(0xffffffffu, (int)pass, i, L) != 0;
                 if (ps && (bi < 0 || v < bpm)) { bi = i; bpm = v; }
+                if (i > 0 && v < mpm) { mi = i; mpm = v; }
             }
             if (bi < 0) {
                 if (a.use_crc) flags |= kInfoCrcFail;
-                bi = 0;
-                bpm = __shfl_sync(0xffffffffu, pm, 0, L);
-#pragma unroll
-                for (int i = 1; i < L; i++) {
-                    const real v = __shfl_sync(0xffffffffu, pm, i, L);
-                    if (v < bpm) { bi = i; bpm = v; }
-                }
+                bi = mi;
             }
             best = bi;
         }
