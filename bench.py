@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the polar decoding hot path on B200 (contract in the task statement).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          (N>1: launched by torch.distributed.run, one rank per GPU)
+  python bench.py --impl reference ...                          (the reference's own CPU code on the host cores)
+
+Metric (BASELINE.json): decoded information Gbit/s for CA-SCL L=8 N=1024 (CRC-24, K=512) -- `value` -- and for BP N=1024,
+100 sweeps -- the `bp_1024` object of the same line.  A step = one pass of the decode kernel over one batch of synthetic
+frames (Philox channel kernel at the Eb/N0 of SURVEY 8d) already resident in HBM; the batch (256 MB / 128 MB of LLRs) is
+larger than the 126 MB L2, so successive steps re-read it from HBM.  `e2e` = the same metric through the C-ABI call a host
+makes (pg_decode_llr_packed) with pinned HOST buffers: H2D copy of the LLRs, decode, D2H copy of the packed decisions and
+per-frame flags, every step.  Timing: CUDA events on the library's stream, barrier + synchronize on both sides, max over ranks.
+Roofline: the path is ALU-bound: achieved = frames x algorithmic lane-ops per frame / kernel time against
+148 SMs x 128 lanes x sm_max_mhz (MEASURED_PEAKS.json); HBM GB/s of the streamed LLRs is reported beside it."""
+import argparse
+import ctypes as C
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N, K_INFO = 1024, 512
+OPS_CASCL = 30016 * 27 + 35906 * 2 + 11185 * 11 + 533 * 160 + 36000 + 28000   # ~1.15 M lane-ops / frame
+OPS_BP_SWEEP = 573440                                                          # per sweep, N=1024
+EBN0_CASCL, EBN0_BP = 2.0, 2.5
+B_CASCL, B_BP = 1 << 16, 1 << 15                                               # frames per step (256 MB / 128 MB of fp32 LLRs)
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return p, "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md recipe)"""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu):
+        self.gpu, self.lines, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ CPU arms (oracle/_ref = the compiled reference)
+def _cpu_worker(args):
+    kind, prog, nframes, seed, ebn0 = args
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import Oracle, RefHarness, awgn_llr
+    rng = np.random.default_rng(seed)
+    llr = awgn_llr(rng, N, nframes, ebn0)           # all-zero codeword + AWGN: decoding work does not depend on the payload
+    dec = RefHarness(prog) if kind == "reference" else Oracle(prog)
+    t = time.perf_counter()
+    out = dec.decode(llr)
+    dt = time.perf_counter() - t
+    out = out[0] if isinstance(out, tuple) else out
+    return dt, int((out != 0).any(1).sum())
+
+
+def cpu_arm(prog, ebn0, frames_per_core, cores=None):
+    """frames/s of the reference decoder on `cores` host cores (one process per core), bounded sample"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import have_ref, build_port
+    kind = "reference" if have_ref(prog) else "port"
+    if kind == "port":
+        build_port()
+    cores = cores or len(os.sched_getaffinity(0)) or 1
+    ctx = mp.get_context("spawn")
+    t = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, [(kind, prog, frames_per_core, 1000 + i, ebn0) for i in range(cores)])
+    wall = time.perf_counter() - t
+    busy = max(r[0] for r in res)                    # slowest worker = time for all cores to finish their share
+    fps = cores * frames_per_core / busy
+    return {"kind": kind, "cores": cores, "frames": cores * frames_per_core, "seconds": busy, "wall": wall, "fps": fps,
+            "block_errors": sum(r[1] for r in res)}
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    fpc = 24                                          # frames per core per step: ~0.2 s of CASCL_1024_L8 on one core
+    for _ in range(a.warmup):
+        cpu_arm("CASCL_1024_L8", EBN0_CASCL, 4)
+    t0 = time.perf_counter()
+    fps, r = [], None
+    for _ in range(a.steps):
+        r = cpu_arm("CASCL_1024_L8", EBN0_CASCL, fpc)
+        fps.append(r["fps"])
+    ms = (time.perf_counter() - t0) * 1e3 / max(1, a.steps)
+    f = sum(fps) / len(fps)
+    rb = cpu_arm("BP_1024", EBN0_BP, 3)
+    val = f * K_INFO / 1e9
+    line = {"impl": "reference", "metric": "decoded info Gbps: CA-SCL L=8 N=1024 (K=512, CRC-24)", "value": val, "unit": "Gbit/s",
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "CASCL_1024_L8 decode (CASCL(), N=1024 K=512 r=24 L=8) at Eb/N0 %.1f dB" % EBN0_CASCL,
+                       "frames_per_step": r["frames"], "host": "reference C decoder, one process per core"},
+            "frames_per_s": f,
+            "cpu_baseline": {"value": val, "unit": "Gbit/s", "cores": r["cores"], "kind": r["kind"],
+                             "sample": "%d frames per core per step, %d steps, unmodified CASCL() compiled -O2 from the reference source" % (fpc, a.steps)},
+            "bp_1024": {"value": rb["fps"] * K_INFO / 1e9, "unit": "Gbit/s", "frames_per_s": rb["fps"], "cores": rb["cores"], "kind": rb["kind"],
+                        "sample": "%d frames per core, BP() 100 sweeps" % 3},
+            "e2e": {"value": val, "unit": "Gbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ GPU arm
+def timed_steps(torch, dist, world, ext_stream, fn, steps, warmup):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext_stream)
+    for _ in range(steps):
+        fn()
+    e1.record(ext_stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.barrier()
+        ms = float(t.item())
+    return ms
+
+
+def wall_steps(torch, dist, world, fn, steps, warmup):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.barrier()
+        ms = float(t.item())
+    return ms
+
+
+def run_gpu_arm(a):
+    import torch
+    import torch.distributed as dist
+    from polardecoding_b200 import Engine
+    from polardecoding_b200.capi import comm_unique_id
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pk, pk_src = peaks()
+    peak_ops = 148 * 128 * pk["sm_max_mhz"] * 1e6
+    sampler = ClockSampler(local)
+    launches = 0
+    res = {}
+
+    def bench_one(prog, ebn0, B, ops_per_frame, **over):
+        nonlocal launches
+        eng = Engine(prog, real="f32", device=local, rank=rank, nranks=world, seed=1024, data_mode=0, **over)
+        if world > 1:  # the library's own NCCL communicator: the id travels over torch.distributed
+            ids = [comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            eng.comm_init(ids[0])
+        st = torch.cuda.ExternalStream(eng.stream_ptr())
+        llr = torch.empty(B * N, dtype=torch.float32, device="cuda")
+        truth = torch.empty(B * (N // 32), dtype=torch.int32, device="cuda")
+        info = torch.empty(B, dtype=torch.int32, device="cuda")
+        first = (1 << 32) + rank * B                                  # disjoint Philox frame ranges per rank
+        eng.channel_device(ebn0, first, B, llr.data_ptr(), truth.data_ptr())
+        eng.sync()
+        l0 = eng.launches()
+        eng.counters_read(reset=True)
+        ms = timed_steps(torch, dist, world, st, lambda: eng.decode_count_device(llr.data_ptr(), B, truth.data_ptr(), None, info.data_ptr()), a.steps, a.warmup)
+        cnt = eng.counters_read(reset=True)
+        if world > 1:
+            cnt = eng.allreduce_counters(cnt)                          # the one collective of the path: final counters
+        launches += eng.launches() - l0
+        per_step = ms / a.steps
+        fps = world * B / (per_step * 1e-3)
+        steps_total = a.steps + a.warmup
+        sweeps = cnt.bp_sweeps / max(1, cnt.frames)
+        ops = ops_per_frame if ops_per_frame else OPS_BP_SWEEP * sweeps
+        out = {"frames_per_s": fps, "gbps": fps * K_INFO / 1e9, "ms_per_step": per_step, "frames_per_step": world * B,
+               "fer": cnt.err_blocks / max(1, cnt.frames), "frames_counted": int(cnt.frames), "tie_frames": int(cnt.tie_frames),
+               "sweeps_per_frame": sweeps,
+               "roofline": {"bound": "alu", "achieved": (fps / world) * ops / 1e12, "peak": peak_ops / 1e12, "unit": "Tlaneop/s",
+                            "frac": (fps / world) * ops / peak_ops, "traffic": None, "ops_per_frame": ops, "peak_source": pk_src + " sm_max_mhz x 148 SMs x 128 lanes",
+                            "hbm_gbs": (fps / world) * (N * 4 + 2 * (N // 8) + 4) / 1e9, "hbm_frac": (fps / world) * (N * 4 + 2 * (N // 8) + 4) / 1e9 / pk["hbm_gbs"]}}
+        assert cnt.frames == world * B * steps_total, (cnt.frames, world, B, steps_total)
+        # ---- e2e: host LLRs (pinned) -> C ABI -> host decisions, every step
+        Be = B // 4
+        h_llr = torch.empty(Be * N, dtype=torch.float32).pin_memory()
+        h_llr.copy_(llr[: Be * N])
+        h_out = torch.empty(Be * (N // 32), dtype=torch.int32).pin_memory()
+        h_flags = torch.empty(Be, dtype=torch.int32).pin_memory()
+        l0 = eng.launches()
+        ms_e = wall_steps(torch, dist, world, lambda: eng.decode_llr_host_ptr(h_llr.data_ptr(), False, Be, h_out.data_ptr(), h_flags.data_ptr()), a.steps, max(1, a.warmup))
+        launches += eng.launches() - l0
+        fps_e = world * Be / (ms_e / a.steps * 1e-3)
+        out["e2e"] = {"value": fps_e * K_INFO / 1e9, "unit": "Gbit/s", "h2d_bytes_per_step": Be * N * 4, "d2h_bytes_per_step": Be * (N // 8) + Be * 4,
+                      "frames_per_s": fps_e, "frames_per_step": world * Be}
+        eng.close()
+        del llr, truth, info
+        return out
+
+    sampler.start()
+    res["cascl"] = bench_one("CASCL_1024_L8", EBN0_CASCL, B_CASCL, OPS_CASCL)
+    res["bp"] = bench_one("BP_1024", EBN0_BP, B_BP, OPS_BP_SWEEP * 100)
+    res["bp_stop"] = bench_one("BP_1024", EBN0_BP, B_BP, 0, bp_early_stop=1)
+    clocks = sampler.stop()
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu:
+        c = cpu_arm("CASCL_1024_L8", EBN0_CASCL, 160)                 # ~1.4 s per core... bounded: ~10-20 s of CPU work in total
+        cb = cpu_arm("BP_1024", EBN0_BP, 6)
+        cpu = {"value": c["fps"] * K_INFO / 1e9, "unit": "Gbit/s", "cores": c["cores"], "kind": c["kind"], "frames_per_s": c["fps"],
+               "sample": "%d frames of CASCL_1024_L8 per core at %.1f dB (%.1f s), unmodified reference CASCL() compiled -O2" % (160, EBN0_CASCL, c["seconds"]),
+               "bp_1024": {"value": cb["fps"] * K_INFO / 1e9, "frames_per_s": cb["fps"], "sample": "6 frames per core, BP() 100 sweeps (%.1f s)" % cb["seconds"]}}
+    if rank == 0:
+        r = res["cascl"]
+        line = {"metric": "decoded info Gbps: CA-SCL L=8 N=1024 (K=512, CRC-24)", "value": r["gbps"], "unit": "Gbit/s", "n_gpus": world,
+                "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "CASCL_1024_L8 (N=1024 K=512 r=24 L=8) at Eb/N0 %.1f dB, PN-63 payload, Philox AWGN" % EBN0_CASCL,
+                           "frames_per_step": r["frames_per_step"], "l2": "inputs larger than L2 (256 MB of LLRs per GPU per step)",
+                           "arith": "fp32 throughput mode; fp64 parity mode is bit-exact with the reference (tests/test_gpu_parity.py)",
+                           "partition": "rank r decodes its own Philox frame range; one NCCL all-reduce of the final counters"},
+                "frames_per_s": r["frames_per_s"], "fer": r["fer"], "tie_frames": r["tie_frames"], "frames_counted": r["frames_counted"],
+                "roofline": r["roofline"], "e2e": r["e2e"], "gpu_launches": launches, "clocks": clocks,
+                "bp_1024": {"value": res["bp"]["gbps"], "unit": "Gbit/s", "frames_per_s": res["bp"]["frames_per_s"], "ms_per_step": res["bp"]["ms_per_step"],
+                            "frames_per_step": res["bp"]["frames_per_step"], "sweeps": 100, "fer": res["bp"]["fer"], "roofline": res["bp"]["roofline"],
+                            "e2e": res["bp"]["e2e"],
+                            "fixed_point_stop": {"value": res["bp_stop"]["gbps"], "frames_per_s": res["bp_stop"]["frames_per_s"],
+                                                 "sweeps_per_frame": res["bp_stop"]["sweeps_per_frame"], "fer": res["bp_stop"]["fer"],
+                                                 "roofline": res["bp_stop"]["roofline"], "note": "same decisions as 100 sweeps (bit-exact stop)"}}}
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_gpu_arm(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -105,11 +105,21 @@ int pg_decode_llr_packed(pg_ctx *ctx, const void *llr, int llr_is_f64, size_t B,
 /* same with DEVICE pointers and packed output (u_hat_packed: [B][N/32] words); no copies, asynchronous on the ctx stream */
 int pg_decode_llr_device(pg_ctx *ctx, const void *d_llr, int llr_is_f64, size_t B, uint32_t *d_u_hat_packed, uint32_t *d_flags);
 
+/* device-resident variant with the on-device error count: d_truth_packed ([B][N/32], e.g. from pg_channel_device) is
+ * compared on the counted positions; block/bit errors, tie and CRC-fail frames are ADDED to the context's device
+ * counters (read with pg_counters_read).  d_u_hat_packed / d_frame_info may be NULL.  Asynchronous on the ctx stream. */
+int pg_decode_count_device(pg_ctx *ctx, const void *d_llr, int llr_is_f64, size_t B, const uint32_t *d_truth_packed,
+                           uint32_t *d_u_hat_packed, uint32_t *d_frame_info);
+int pg_counters_read(pg_ctx *ctx, pg_counters *out, int reset); /* synchronises the ctx stream */
+
 /* ---- fused channel: payload, CRC, polar encode, BPSK, AWGN, LLR for frames [first_frame, first_frame+B) ----
  * Noise comes from Philox4x32-10 with key = seed and counter = (global frame index, position/4): the result for a
  * frame does not depend on B, on the batch split or on the rank that produces it.
  * llr_out [B][N] (context's arithmetic type: float or double), u_out [B][N] bytes; HOST pointers, may be NULL. */
 int pg_channel(pg_ctx *ctx, double ebn0_db, uint64_t first_frame, size_t B, void *llr_out, uint8_t *u_out);
+
+/* same into DEVICE buffers (d_llr: [B][N] of the context's type; d_u_packed: [B][N/32] words; either may be NULL) */
+int pg_channel_device(pg_ctx *ctx, double ebn0_db, uint64_t first_frame, size_t B, void *d_llr, uint32_t *d_u_packed);
 
 /* ---- Monte-Carlo point: channel + decode + on-device error count -------------------------------------
  * Simulates frames first_frame + rank*chunk + i ... in rounds of nranks*chunk frames (chunk = frames one rank
@@ -138,6 +148,18 @@ int pg_bpr_reset(pg_ctx *ctx);
 int pg_comm_unique_id(void *id128);
 int pg_comm_init(pg_ctx *ctx, const void *id128);
 int pg_allreduce_counters(pg_ctx *ctx, pg_counters *c); /* in place, sum over ranks */
+
+/* ---- the host-side rules pg_simulate applies, exported so that other hosts and CPU tests can use them --------
+ * pg_partition: frames of `rank` in the round that starts at global frame round_first: rank q owns
+ *   [round_first + q*chunk, +chunk), clipped to `budget` frames left in the run (count may be 0).
+ * pg_merge_round: walk the ranks' counters of one round in global frame order, adding them to *acc.  If exact_stop and
+ *   the target-th block error falls into rank q's chunk: stop BEFORE adding q, return *cut_rank = q and *need = block
+ *   errors still missing; rank q then calls pg_truncate_info on its per-frame results and every rank adds that part.
+ * pg_truncate_info: counters of the shortest prefix of frame_info[] that holds `need` block errors (frame_info words
+ *   as written by the kernels: bits 0..15 wrong bits, bit 16 tie, bit 17 CRC fail, bits 24..31 BP sweeps). */
+int pg_partition(uint64_t round_first, uint64_t chunk, int nranks, int rank, uint64_t budget, uint64_t *start, uint64_t *count);
+int pg_merge_round(const pg_counters *round, int nranks, uint64_t target, int exact_stop, pg_counters *acc, int *cut_rank, uint64_t *need);
+int pg_truncate_info(const uint32_t *frame_info, size_t nframes, uint64_t need, pg_counters *part);
 
 /* ---- introspection for benches ------------------------------------------------------------------------ */
 int pg_sync(pg_ctx *ctx);                              /* cudaStreamSynchronize on the ctx stream */

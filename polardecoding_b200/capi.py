@@ -55,6 +55,9 @@ def load_library():
     lib.pg_decode_llr.argtypes = [vp, vp, C.c_int, C.c_size_t, vp, vp]
     lib.pg_decode_llr_packed.argtypes = [vp, vp, C.c_int, C.c_size_t, vp, vp]
     lib.pg_decode_llr_device.argtypes = [vp, vp, C.c_int, C.c_size_t, vp, vp]
+    lib.pg_decode_count_device.argtypes = [vp, vp, C.c_int, C.c_size_t, vp, vp, vp]
+    lib.pg_counters_read.argtypes = [vp, C.POINTER(PgCounters), C.c_int]
+    lib.pg_channel_device.argtypes = [vp, C.c_double, C.c_uint64, C.c_size_t, vp, vp]
     lib.pg_channel.argtypes = [vp, C.c_double, C.c_uint64, C.c_size_t, vp, vp]
     lib.pg_simulate.argtypes = [vp, C.c_double, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(PgCounters)]
     lib.pg_simulate_batch.argtypes = [vp, C.c_double, C.c_uint64, C.c_size_t, C.POINTER(PgCounters), vp]
@@ -157,6 +160,32 @@ class Engine:
         rc = self.lib.pg_simulate(self.ctx, float(ebn0_db), int(first_frame), int(target_err_blocks), int(max_frames), int(bool(exact_stop)), C.byref(out))
         self._check(rc, "pg_simulate")
         return out
+
+    # ---- device-pointer calls (pointers are plain integers, e.g. torch.Tensor.data_ptr())
+    def channel_device(self, ebn0_db, first_frame, B, d_llr, d_u_packed):
+        self._check(self.lib.pg_channel_device(self.ctx, float(ebn0_db), int(first_frame), B, d_llr, d_u_packed), "pg_channel_device")
+
+    def decode_count_device(self, d_llr, B, d_truth, d_u_hat=None, d_info=None):
+        self._check(self.lib.pg_decode_count_device(self.ctx, d_llr, int(self.f64), B, d_truth, d_u_hat, d_info), "pg_decode_count_device")
+
+    def decode_llr_device(self, d_llr, llr_is_f64, B, d_u_hat=None, d_flags=None):
+        self._check(self.lib.pg_decode_llr_device(self.ctx, d_llr, int(llr_is_f64), B, d_u_hat, d_flags), "pg_decode_llr_device")
+
+    def counters_read(self, reset=False):
+        out = PgCounters()
+        self._check(self.lib.pg_counters_read(self.ctx, C.byref(out), int(reset)), "pg_counters_read")
+        return out
+
+    def decode_llr_host_ptr(self, llr_ptr, llr_is_f64, B, out_packed_ptr, flags_ptr=None):
+        """pg_decode_llr_packed on raw host pointers (pinned buffers owned by the caller)"""
+        self._check(self.lib.pg_decode_llr_packed(self.ctx, llr_ptr, int(llr_is_f64), B, out_packed_ptr, flags_ptr), "pg_decode_llr_packed")
+
+    def stream_ptr(self):
+        return int(self.lib.pg_stream(self.ctx) or 0)
+
+    def allreduce_counters(self, c):
+        self._check(self.lib.pg_allreduce_counters(self.ctx, C.byref(c)), "pg_allreduce_counters")
+        return c
 
     def bpr_config(self, samples):
         arr = (C.c_int * len(samples))(*samples)

@@ -309,12 +309,12 @@ static int debug_sync(pg_ctx *ctx, const char *what)
     return PG_OK;
 }
 
-static int run_channel(pg_ctx *ctx, double ebn0_db, uint64_t first, size_t B, bool want_llr)
+static int run_channel_to(pg_ctx *ctx, double ebn0_db, uint64_t first, size_t B, void *d_llr, uint32_t *d_truth)
 {
     ChannelArgs a;
     std::memset(&a, 0, sizeof(a));
-    a.llr = want_llr ? ctx->d_llr : nullptr;
-    a.u_packed = ctx->d_truth;
+    a.llr = d_llr;
+    a.u_packed = d_truth;
     a.I = ctx->d_I;
     a.crc_sys = ctx->d_crc_sys;
     a.first_frame = first; a.B = B;
@@ -329,6 +329,11 @@ static int run_channel(pg_ctx *ctx, double ebn0_db, uint64_t first, size_t B, bo
     ctx->ev_ch = true;
     ctx->launches++;
     return debug_sync(ctx, "channel");
+}
+
+static int run_channel(pg_ctx *ctx, double ebn0_db, uint64_t first, size_t B, bool want_llr)
+{
+    return run_channel_to(ctx, ebn0_db, first, B, want_llr ? ctx->d_llr : nullptr, ctx->d_truth);
 }
 
 static int run_decode(pg_ctx *ctx, const void *d_llr, size_t B, const uint32_t *d_truth, uint32_t *d_uhat, uint32_t *d_info, bool count)
@@ -383,6 +388,35 @@ extern "C" int pg_decode_llr_device(pg_ctx *ctx, const void *d_llr, int llr_is_f
         src = ctx->d_llr;
     }
     return run_decode(ctx, src, B, nullptr, d_u_hat_packed, d_flags, false);
+}
+
+extern "C" int pg_decode_count_device(pg_ctx *ctx, const void *d_llr, int llr_is_f64, size_t B, const uint32_t *d_truth_packed,
+                                      uint32_t *d_u_hat_packed, uint32_t *d_frame_info)
+{
+    if (!ctx || !d_llr) return PG_ERR_ARG;
+    if (B == 0) return PG_OK;
+    CU(cudaSetDevice(ctx->p.device));
+    if ((llr_is_f64 != 0) != ctx->f64) { ctx->err = "pg_decode_count_device: LLR type must be the context's arithmetic type"; return PG_ERR_ARG; }
+    return run_decode(ctx, d_llr, B, d_truth_packed, d_u_hat_packed, d_frame_info, true);
+}
+
+extern "C" int pg_counters_read(pg_ctx *ctx, pg_counters *out, int reset)
+{
+    if (!ctx || !out) return PG_ERR_ARG;
+    CU(cudaSetDevice(ctx->p.device));
+    CU(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, CNT_N * 8, cudaMemcpyDeviceToHost, ctx->st));
+    if (reset) CU(cudaMemsetAsync(ctx->d_counters, 0, CNT_N * 8, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    std::memcpy(out, ctx->h_counters, CNT_N * 8);
+    return PG_OK;
+}
+
+extern "C" int pg_channel_device(pg_ctx *ctx, double ebn0_db, uint64_t first_frame, size_t B, void *d_llr, uint32_t *d_u_packed)
+{
+    if (!ctx) return PG_ERR_ARG;
+    if (B == 0) return PG_OK;
+    CU(cudaSetDevice(ctx->p.device));
+    return run_channel_to(ctx, ebn0_db, first_frame, B, d_llr, d_u_packed);
 }
 
 static int decode_host(pg_ctx *ctx, const void *llr, int llr_is_f64, size_t B, uint8_t *u_hat, uint32_t *u_hat_packed, uint32_t *flags)
@@ -503,58 +537,37 @@ extern "C" int pg_simulate(pg_ctx *ctx, double ebn0_db, uint64_t first_frame, ui
     if (!ctx || !out || (target_err_blocks == 0 && max_frames == 0)) return PG_ERR_ARG;
     CU(cudaSetDevice(ctx->p.device));
     const int R = ctx->p.nranks, me = ctx->p.rank;
+    static_assert(sizeof(pg_counters) == CNT_N * 8, "pg_counters layout");
     std::memset(out, 0, sizeof(*out));
     uint64_t next = first_frame;  // first global frame of the next round
     size_t chunk = std::min<size_t>(ctx->chunk_max, 4096);
-    std::vector<unsigned long long> xc((size_t)R * CNT_N);
+    std::vector<pg_counters> xc((size_t)R);
     while (true) {
-        // frames of this round: rank q takes [next + q*chunk, next + (q+1)*chunk) clipped to the frame budget
-        uint64_t budget = max_frames ? (max_frames - out->frames) : ~0ull;
+        const uint64_t budget = max_frames ? (max_frames - out->frames) : ~0ull;
         if (max_frames && budget == 0) break;
-        auto rank_count = [&](int q) -> size_t {
-            const uint64_t lo = (uint64_t)q * chunk;
-            if (lo >= budget) return 0;
-            return (size_t)std::min<uint64_t>(chunk, budget - lo);
-        };
-        const size_t mine = rank_count(me);
-        std::fill(xc.begin(), xc.end(), 0ull);
+        uint64_t start = 0, mine = 0;
+        pg_partition(next, chunk, R, me, budget, &start, &mine);
+        std::memset(xc.data(), 0, sizeof(pg_counters) * xc.size());
         if (mine) {
-            int rc = simulate_chunk(ctx, ebn0_db, next + (uint64_t)me * chunk, mine, exact_stop != 0);
+            int rc = simulate_chunk(ctx, ebn0_db, start, (size_t)mine, exact_stop != 0);
             if (rc) return rc;
-            std::memcpy(&xc[(size_t)me * CNT_N], ctx->h_counters, CNT_N * 8);
+            std::memcpy(&xc[me], ctx->h_counters, CNT_N * 8);
         }
-        int rc = exchange(ctx, xc.data(), xc.size());
+        int rc = exchange(ctx, reinterpret_cast<unsigned long long *>(xc.data()), xc.size() * CNT_N);
         if (rc) return rc;
-        // walk the ranks in global frame order
-        bool done = false;
-        for (int q = 0; q < R && !done; q++) {
-            const unsigned long long *c = &xc[(size_t)q * CNT_N];
-            if (exact_stop && target_err_blocks && out->err_blocks + c[CNT_ERR_BLOCKS] >= target_err_blocks) {
-                // the target-th block error falls into rank q's chunk: that rank truncates, everybody learns the result
-                unsigned long long part[CNT_N];
-                std::memset(part, 0, sizeof(part));
-                if (q == me) {
-                    const uint64_t need = target_err_blocks - out->err_blocks;
-                    uint64_t seen = 0;
-                    size_t i = 0;
-                    for (; i < mine && seen < need; i++) {
-                        const uint32_t w = ctx->h_info[i];
-                        part[CNT_FRAMES]++;
-                        if (w & 0xFFFFu) { part[CNT_ERR_BLOCKS]++; part[CNT_ERR_BITS] += (w & 0xFFFFu); seen++; }
-                        if (w & kInfoTie) part[CNT_TIE]++;
-                        if (w & kInfoCrcFail) part[CNT_CRCFAIL]++;
-                        part[CNT_SWEEPS] += (w >> 24);
-                    }
-                }
-                rc = exchange(ctx, part, CNT_N);
-                if (rc) return rc;
-                add_counters(out, part);
-                done = true;
-            } else {
-                add_counters(out, c);
-            }
+        int cut = -1;
+        uint64_t need = 0;
+        pg_merge_round(xc.data(), R, target_err_blocks, exact_stop, out, &cut, &need);
+        if (cut >= 0) {
+            // the target-th block error fell into rank `cut`'s chunk: that rank truncates, everybody learns the result
+            pg_counters part;
+            std::memset(&part, 0, sizeof(part));
+            if (cut == me) pg_truncate_info(ctx->h_info, (size_t)mine, need, &part);
+            rc = exchange(ctx, reinterpret_cast<unsigned long long *>(&part), CNT_N);
+            if (rc) return rc;
+            add_counters(out, reinterpret_cast<unsigned long long *>(&part));
+            break;
         }
-        if (done) break;
         if (target_err_blocks && out->err_blocks >= target_err_blocks) break;
         if (max_frames && out->frames >= max_frames) break;
         next += (uint64_t)R * chunk;
