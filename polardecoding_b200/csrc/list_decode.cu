@@ -9,7 +9,8 @@
 //  * A warp decodes 32/L frames side by side; lane = (frame, path slot k).  All lanes run the SAME
 //    instruction stream (the SC schedule does not depend on data), so there is no divergence, and
 //    every f/g evaluation of a path is lane-private: no barrier inside a path, ILP from the 4-wide
-//    unrolled layers.  Paths that do not exist yet (list filling) carry PM=+inf and read path 0's data.
+//    unrolled layers.  Slots that hold no path yet (list filling) carry PM=+inf and are exact copies
+//    of path 0, so they compute finite values and never win a comparison.
 //  * Array formulation: at bit j, t=ctz(j): one g-layer at stage t then f-layers t-1..0; stage s keeps
 //    2^s live LLRs.  Stages 0..2 live in registers (a fully unrolled 4-leaf subtree), stages
 //    3..SMEM_TOP-1 in shared memory, the rest in an L2-resident global scratch, all laid out
@@ -19,10 +20,11 @@
 //    2^s), always into the home array, so a clone is a register shuffle of the pointer word -- the
 //    reference copies the whole graph instead (copyPath/simpleCopy, 74 % of its run time).
 //  * Partial sums are kept as packed bit vectors per stage (B[s], 2^s bits) with the same pointer
-//    scheme; stages 2..5 are registers.  The final B[n] is the re-encoded codeword, u_hat = B[n] F^{(x)n}.
+//    scheme; stages 2..5 are registers, 6..BITS_TOP-1 shared memory, the rest global scratch.
+//    The final B[n] is the re-encoded codeword, u_hat = B[n] F^{(x)n}.
 //  * List pruning: each lane ranks its two candidates against the 2L candidates of its frame with
 //    shuffles.  If all candidates are distinct (checked with one warp reduction) rank < L is exactly
-//    the reference's "PM < med"; otherwise (exact ties, or +inf dummies while the list fills) a slow
+//    the reference's "PM < med"; otherwise (exact ties, or +inf slots while the list fills) a slow
 //    path applies the total order (value, candidate index) and flags frames where the reference's
 //    rule would have been ambiguous ("Oops!", SCL_1024.c:621).
 #include "engine.h"
@@ -35,42 +37,60 @@ template <typename real> struct alignas(16) vec4 { real v[4]; };
 template <int L> struct ptr_word { using type = uint32_t; static constexpr int W = 4; };
 template <> struct ptr_word<32> { using type = unsigned long long; static constexpr int W = 5; };
 
-template <typename T>
-__device__ __forceinline__ T shfl_any(T v, int src)
-{
-    return __shfl_sync(0xffffffffu, v, src);
-}
-
-template <typename real, int LOGN, int L, int SMEM_TOP>
+template <typename real, int LOGN, int L, int SMEM_TOP, int BITS_TOP>
 struct ListCfg {
     static constexpr int N = 1 << LOGN;
     static constexpr int W = (N + 31) / 32;
     static constexpr int FPW = 32 / L;
-    static constexpr int TOP = (SMEM_TOP < LOGN) ? SMEM_TOP : LOGN;  // stages 3..TOP-1 in smem
-    // reals of shared memory for the stage arrays, words for the bit arrays (stages 6..LOGN)
+    static constexpr int TOP = (SMEM_TOP < LOGN) ? SMEM_TOP : LOGN;            // LLR stages 3..TOP-1 in smem
+    static constexpr int BTOP = (BITS_TOP < LOGN + 1) ? BITS_TOP : LOGN + 1;    // bit stages 6..BTOP-1 in smem
+    static constexpr int BLO = (BTOP > 6) ? BTOP : 6;                           // first bit stage in global scratch
     static constexpr int SM_STAGE_REALS = 32 * ((1 << TOP) - 8);
-    static constexpr int SM_BIT_WORDS = (LOGN >= 6) ? 32 * ((1 << (LOGN - 4)) - 2) : 0;
+    static constexpr int SM_BIT_WORDS = (BTOP > 6) ? 32 * ((1 << (BTOP - 5)) - 2) : 0;
     static constexpr size_t SMEM = (size_t)SM_STAGE_REALS * sizeof(real) + (size_t)SM_BIT_WORDS * 4;
-    static constexpr size_t GS_REALS = 32 * (size_t)((1 << LOGN) - (1 << TOP));  // stages TOP..LOGN-1
+    static constexpr size_t GS_REALS = 32 * (size_t)((1 << LOGN) - (1 << TOP));                    // stages TOP..LOGN-1
+    static constexpr size_t GS_BIT_WORDS = (LOGN >= BLO) ? 32 * (size_t)((1 << (LOGN - 4)) - (1 << (BLO - 5))) : 0;  // BLO..LOGN
+    static constexpr size_t GS_BYTES = GS_REALS * sizeof(real) + GS_BIT_WORDS * 4;
 };
 
-template <typename real, int LOGN, int L, int SMEM_TOP>
+// one CHK / g evaluation of four neighbouring nodes
+template <typename real>
+__device__ __forceinline__ vec4<real> f4(const vec4<real> &x, const vec4<real> &y)
+{
+    vec4<real> o;
+#pragma unroll
+    for (int e = 0; e < 4; e++) o.v[e] = chk<real>(x.v[e], y.v[e]);
+    return o;
+}
+template <typename real>
+__device__ __forceinline__ vec4<real> g4(const vec4<real> &up, const vec4<real> &lo, uint32_t b)
+{
+    vec4<real> o;
+#pragma unroll
+    for (int e = 0; e < 4; e++) o.v[e] = lo.v[e] + real_traits<real>::flip(up.v[e], (b >> e) & 1u);  // SC_128.c:355-359
+    return o;
+}
+
+template <typename real, int LOGN, int L, int SMEM_TOP, int BITS_TOP>
 __global__ void __launch_bounds__(32) list_decode_kernel(const ListArgs a)
 {
-    using C = ListCfg<real, LOGN, L, SMEM_TOP>;
+    using C = ListCfg<real, LOGN, L, SMEM_TOP, BITS_TOP>;
     using RT = real_traits<real>;
     using PW = ptr_word<L>;
     using ptr_t = typename PW::type;
-    constexpr int N = C::N, W = C::W, FPW = C::FPW, TOP = C::TOP;
+    using V4 = vec4<real>;
+    constexpr int N = C::N, W = C::W, FPW = C::FPW, TOP = C::TOP, BTOP = C::BTOP, BLO = C::BLO;
     constexpr int PWID = PW::W;
     constexpr ptr_t PMASK = (ptr_t)((1u << PWID) - 1);
     constexpr uint32_t LMASK = (L == 32) ? 0xffffffffu : ((1u << (L & 31)) - 1u);  // lanes of one frame
     const real INF = RT::inf();
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    real *sm_stage = reinterpret_cast<real *>(smem_raw);
-    uint32_t *sm_bits = reinterpret_cast<uint32_t *>(smem_raw + (size_t)C::SM_STAGE_REALS * sizeof(real));
-    real *gs_stage = reinterpret_cast<real *>(a.gscratch) + (size_t)blockIdx.x * C::GS_REALS;
+    V4 *const sm_stage = reinterpret_cast<V4 *>(smem_raw);  // stage s (3<=s<TOP): group i4 of lane pl at [8*(2^s-8) + i4*32 + pl]
+    uint32_t *const sm_bits = reinterpret_cast<uint32_t *>(smem_raw + (size_t)C::SM_STAGE_REALS * sizeof(real));
+    unsigned char *const gs_raw = reinterpret_cast<unsigned char *>(a.gscratch) + (size_t)blockIdx.x * C::GS_BYTES;
+    V4 *const gs_stage = reinterpret_cast<V4 *>(gs_raw);
+    uint32_t *const gs_bits = reinterpret_cast<uint32_t *>(gs_raw + C::GS_REALS * sizeof(real));
 
     const int lane = threadIdx.x;
     const int k = lane & (L - 1);
@@ -78,108 +98,113 @@ __global__ void __launch_bounds__(32) list_decode_kernel(const ListArgs a)
     const int fl = lane / L;
     const unsigned long long groups = (a.B + FPW - 1) / FPW;
 
-    // stage s array (s>=3), as vec4 groups: element group i4 of physical lane pl is [i4*32 + pl]
-    auto stage4 = [&](int s) -> vec4<real> * {
-        real *base = (s < TOP) ? (sm_stage + 32 * ((1 << s) - 8)) : (gs_stage + 32 * (size_t)((1 << s) - (1 << TOP)));
-        return reinterpret_cast<vec4<real> *>(base);
-    };
-    // bit array of stage s (s>=6): word w of physical lane pl is [w*32 + pl]
-    auto bits_of = [&](int s) -> uint32_t * { return sm_bits + 32 * ((1 << (s - 5)) - 2); };
+    auto sm_stage_at = [&](int s) -> V4 * { return sm_stage + 8 * ((1 << s) - 8); };
+    auto gs_stage_at = [&](int s) -> V4 * { return gs_stage + 8 * (size_t)((1 << s) - (1 << TOP)); };
+    // bit array of stage s (s>=6): word w of physical lane pl at [w*32 + pl]
+    auto sm_bits_at = [&](int s) -> uint32_t * { return sm_bits + 32 * ((1 << (s - 5)) - 2); };
+    auto gs_bits_at = [&](int s) -> uint32_t * { return gs_bits + 32 * (size_t)((1 << (s - 5)) - (1 << (BLO - 5))); };
 
     for (unsigned long long g = blockIdx.x; g < groups; g += gridDim.x) {
         unsigned long long frame = g * FPW + fl;
         const bool valid = frame < a.B;
         if (!valid) frame = a.B - 1;  // tail lanes decode a duplicate and write nothing
-        const vec4<real> *ch4 = reinterpret_cast<const vec4<real> *>(reinterpret_cast<const real *>(a.llr) + frame * (size_t)N);
+        const V4 *const ch4 = reinterpret_cast<const V4 *>(reinterpret_cast<const real *>(a.llr) + frame * (size_t)N);
 
         real s2[4] = {0, 0, 0, 0}, s1[2] = {0, 0}, pm;
-        ptr_t ptr = 0, bptr = 0;  // fields: stage s at (s-3)*PWID / bit stage s at (s-6)*PWID
+        ptr_t ptr = 0, bptr = 0;  // fields: LLR stage s at (s-3)*PWID / bit stage s at (s-6)*PWID
         uint32_t Blow = 0, B5 = 0, ug = 0, flags = 0;
-        pm = (k == 0) ? (real)0 : INF;
-        if (L == 1) pm = (real)0;
+        pm = (k == 0 || L == 1) ? (real)0 : INF;
 
         auto pfield = [&](int s) -> int { return (L == 1) ? 0 : (int)((ptr >> ((s - 3) * PWID)) & PMASK); };
         auto bfield = [&](int s) -> int { return (L == 1) ? 0 : (int)((bptr >> ((s - 6) * PWID)) & PMASK); };
-        auto set_pfield = [&](int s, int v) {
-            if (L > 1) ptr = (ptr & ~(PMASK << ((s - 3) * PWID))) | ((ptr_t)v << ((s - 3) * PWID));
+        auto set_pfield = [&](int s) {
+            if (L > 1) ptr = (ptr & ~(PMASK << ((s - 3) * PWID))) | ((ptr_t)k << ((s - 3) * PWID));
         };
-        auto set_bfield = [&](int s, int v) {
-            if (L > 1) bptr = (bptr & ~(PMASK << ((s - 6) * PWID))) | ((ptr_t)v << ((s - 6) * PWID));
+        auto set_bfield = [&](int s) {
+            if (L > 1) bptr = (bptr & ~(PMASK << ((s - 6) * PWID))) | ((ptr_t)k << ((s - 6) * PWID));
         };
 
-
-        // ---- f-layer producing stage s (3 <= s < LOGN) from stage s+1 ------------------------------------
+        // ---- f-layer producing stage s (3 <= s < LOGN) from stage s+1, into the HOME array ----------------
         auto f_layer = [&](int s) {
-            const bool alive = pm < INF;
             const int cnt4 = 1 << (s - 2);
-            vec4<real> *dst = stage4(s) + lane;
-            if (s + 1 == LOGN) {
+            if (s < TOP) {
+                V4 *dst = sm_stage_at(s) + lane;
+                if (s + 1 == LOGN) {
 #pragma unroll 2
-                for (int i4 = 0; i4 < cnt4; i4++) {
-                    const vec4<real> x = ch4[i4], y = ch4[i4 + cnt4];
-                    vec4<real> o;
-#pragma unroll
-                    for (int e = 0; e < 4; e++) o.v[e] = chk<real>(x.v[e], y.v[e]);
-                    if (alive) dst[i4 * 32] = o;
+                    for (int i4 = 0; i4 < cnt4; i4++) dst[i4 * 32] = f4<real>(ch4[i4], ch4[i4 + cnt4]);
+                } else if (s + 1 < TOP) {
+                    const V4 *src = sm_stage_at(s + 1) + fbase + pfield(s + 1);
+#pragma unroll 2
+                    for (int i4 = 0; i4 < cnt4; i4++) dst[i4 * 32] = f4<real>(src[i4 * 32], src[(i4 + cnt4) * 32]);
+                } else {
+                    const V4 *src = gs_stage_at(s + 1) + fbase + pfield(s + 1);
+#pragma unroll 2
+                    for (int i4 = 0; i4 < cnt4; i4++) dst[i4 * 32] = f4<real>(src[i4 * 32], src[(i4 + cnt4) * 32]);
                 }
             } else {
-                const vec4<real> *src = stage4(s + 1) + fbase + pfield(s + 1);
+                V4 *dst = gs_stage_at(s) + lane;
+                if (s + 1 == LOGN) {
 #pragma unroll 2
-                for (int i4 = 0; i4 < cnt4; i4++) {
-                    const vec4<real> x = src[i4 * 32], y = src[(i4 + cnt4) * 32];
-                    vec4<real> o;
-#pragma unroll
-                    for (int e = 0; e < 4; e++) o.v[e] = chk<real>(x.v[e], y.v[e]);
-                    if (alive) dst[i4 * 32] = o;
+                    for (int i4 = 0; i4 < cnt4; i4++) dst[i4 * 32] = f4<real>(ch4[i4], ch4[i4 + cnt4]);
+                } else {
+                    const V4 *src = gs_stage_at(s + 1) + fbase + pfield(s + 1);
+#pragma unroll 2
+                    for (int i4 = 0; i4 < cnt4; i4++) dst[i4 * 32] = f4<real>(src[i4 * 32], src[(i4 + cnt4) * 32]);
                 }
             }
-            set_pfield(s, alive ? k : 0);
+            set_pfield(s);
             __syncwarp();
         };
 
-        // partial-sum bits of stage t for nodes 4*i4 .. 4*i4+3 (t >= 2)
-        auto bits4 = [&](int t, int i4) -> uint32_t {
-            if (t == 2) return Blow & 0xF;
-            if (t == 3) return (Blow >> (4 + 4 * i4)) & 0xF;
-            if (t == 4) return (Blow >> (12 + 4 * i4)) & 0xF;
-            if (t == 5) return (B5 >> (4 * i4)) & 0xF;
-            const uint32_t w = bits_of(t)[(i4 >> 3) * 32 + fbase + bfield(t)];
-            return (w >> ((i4 & 7) * 4)) & 0xF;
-        };
-
-        // ---- g-layer producing stage t (3 <= t < LOGN) from stage t+1 and B[t] ---------------------------
-        auto g_layer = [&](int t) {
-            const bool alive = pm < INF;
+        // ---- g-layer producing stage t (3 <= t < LOGN) from stage t+1 and the partial sums B[t] ------------
+        // `word(w)` returns partial-sum bits 32w..32w+31 of B[t]
+        auto g_run = [&](int t, const V4 *src, int sstride, V4 *dst, auto word) {
             const int cnt4 = 1 << (t - 2);
-            vec4<real> *dst = stage4(t) + lane;
-            const bool from_ch = (t + 1 == LOGN);
-            const vec4<real> *src = from_ch ? ch4 : (stage4(t + 1) + fbase + pfield(t + 1));
-            const int stride = from_ch ? 1 : 32;
+            if (cnt4 >= 8) {
+                for (int w = 0; w < (cnt4 >> 3); w++) {
+                    const uint32_t bw = word(w);
 #pragma unroll 2
-            for (int i4 = 0; i4 < cnt4; i4++) {
-                const vec4<real> up = src[i4 * stride], lo = src[(i4 + cnt4) * stride];
-                const uint32_t b = bits4(t, i4);
-                vec4<real> o;
-#pragma unroll
-                for (int e = 0; e < 4; e++) o.v[e] = lo.v[e] + RT::flip(up.v[e], (b >> e) & 1u);
-                if (alive) dst[i4 * 32] = o;
+                    for (int q = 0; q < 8; q++) {
+                        const int i4 = w * 8 + q;
+                        dst[i4 * 32] = g4<real>(src[i4 * sstride], src[(i4 + cnt4) * sstride], (bw >> (4 * q)) & 0xFu);
+                    }
+                }
+            } else {
+                const uint32_t bw = word(0);
+                for (int i4 = 0; i4 < cnt4; i4++)
+                    dst[i4 * 32] = g4<real>(src[i4 * sstride], src[(i4 + cnt4) * sstride], (bw >> (4 * i4)) & 0xFu);
             }
-            set_pfield(t, alive ? k : 0);
+        };
+        auto g_layer = [&](int t) {
+            auto word = [&](int w) -> uint32_t {
+                if (t == 3) return (Blow >> 4) & 0xFFu;
+                if (t == 4) return (Blow >> 12) & 0xFFFFu;
+                if (t == 5) return B5;
+                if (t < BTOP) return sm_bits_at(t)[w * 32 + fbase + bfield(t)];
+                return gs_bits_at(t)[w * 32 + fbase + bfield(t)];
+            };
+            if (t < TOP) {
+                V4 *dst = sm_stage_at(t) + lane;
+                if (t + 1 == LOGN) g_run(t, ch4, 1, dst, word);
+                else if (t + 1 < TOP) g_run(t, sm_stage_at(t + 1) + fbase + pfield(t + 1), 32, dst, word);
+                else g_run(t, gs_stage_at(t + 1) + fbase + pfield(t + 1), 32, dst, word);
+            } else {
+                V4 *dst = gs_stage_at(t) + lane;
+                if (t + 1 == LOGN) g_run(t, ch4, 1, dst, word);
+                else g_run(t, gs_stage_at(t + 1) + fbase + pfield(t + 1), 32, dst, word);
+            }
+            set_pfield(t);
             __syncwarp();
         };
 
         // stage 3 -> registers (stage 2)
         auto stage2_from3 = [&](bool is_g) {
-            const vec4<real> *src = stage4(3) + fbase + pfield(3);
-            const vec4<real> up = src[0], lo = src[32];
-            if (is_g) {
-                const uint32_t b = Blow & 0xF;
+            V4 up, lo;
+            if (3 < TOP) { const V4 *src = sm_stage_at(3) + fbase + pfield(3); up = src[0]; lo = src[32]; }
+            else { const V4 *src = gs_stage_at(3) + fbase + pfield(3); up = src[0]; lo = src[32]; }
+            const V4 o = is_g ? g4<real>(up, lo, Blow & 0xFu) : f4<real>(up, lo);
 #pragma unroll
-                for (int e = 0; e < 4; e++) s2[e] = lo.v[e] + RT::flip(up.v[e], (b >> e) & 1u);
-            } else {
-#pragma unroll
-                for (int e = 0; e < 4; e++) s2[e] = chk<real>(up.v[e], lo.v[e]);
-            }
+            for (int e = 0; e < 4; e++) s2[e] = o.v[e];
         };
 
         // ---- one leaf: frozen -> PM only; information -> decide (SC) or fork/prune (list) ------------------
@@ -243,8 +268,8 @@ __global__ void __launch_bounds__(32) list_decode_kernel(const ListArgs a)
             for (int e = 0; e < 4; e++) s2[e] = __shfl_sync(0xffffffffu, s2[e], src);
             s1[0] = __shfl_sync(0xffffffffu, s1[0], src);
             s1[1] = __shfl_sync(0xffffffffu, s1[1], src);
-            ptr = shfl_any(ptr, src);
-            bptr = shfl_any(bptr, src);
+            ptr = __shfl_sync(0xffffffffu, ptr, src);
+            bptr = __shfl_sync(0xffffffffu, bptr, src);
             Blow = __shfl_sync(0xffffffffu, Blow, src);
             B5 = __shfl_sync(0xffffffffu, B5, src);
             ug = __shfl_sync(0xffffffffu, ug, src);
@@ -252,7 +277,7 @@ __global__ void __launch_bounds__(32) list_decode_kernel(const ListArgs a)
             if (src != lane) { pm = pc1; u = 1u; }
             else if (k0) { pm = c0; u = 0u; }
             else if (k1) { pm = c1; u = 1u; }
-            else { pm = INF; u = 0u; }
+            else { pm = INF; u = 0u; }  // empty slot: stays a copy of path 0 (which keeps its bit-0 branch while the list fills)
             return u;
         };
 
@@ -304,19 +329,19 @@ __global__ void __launch_bounds__(32) list_decode_kernel(const ListArgs a)
             else if (T == 4) Blow = (Blow & ~0xFFFF000u) | (t32 << 12);
             else if (T == 5) B5 = t32;
             else {
-                const bool alive = pm < INF;
-                uint32_t *dst = bits_of(T) + lane;
-                const uint32_t w0 = B5 ^ t32;
-                if (alive) { dst[0] = w0; dst[32] = t32; }
+                uint32_t *dst = ((T < BTOP) ? sm_bits_at(T) : gs_bits_at(T)) + lane;
+                dst[0] = B5 ^ t32;
+                dst[32] = t32;
                 for (int s = 6; s < T; s++) {
                     const int len = 1 << (s - 5);
-                    const uint32_t *srcb = bits_of(s) + fbase + bfield(s);
+                    const uint32_t *srcb = ((s < BTOP) ? sm_bits_at(s) : gs_bits_at(s)) + fbase + bfield(s);
                     for (int i = 0; i < len; i++) {
                         const uint32_t d = dst[i * 32];
-                        if (alive) { dst[(i + len) * 32] = d; dst[i * 32] = d ^ srcb[i * 32]; }
+                        dst[(i + len) * 32] = d;
+                        dst[i * 32] = d ^ srcb[i * 32];
                     }
                 }
-                set_bfield(T, alive ? k : 0);
+                set_bfield(T);
                 __syncwarp();
             }
         }
@@ -327,7 +352,7 @@ __global__ void __launch_bounds__(32) list_decode_kernel(const ListArgs a)
         if (LOGN == 5) {
             xw[0] = B5;
         } else {
-            const uint32_t *srcb = bits_of(LOGN) + fbase + bfield(LOGN);
+            const uint32_t *srcb = ((LOGN < BTOP) ? sm_bits_at(LOGN) : gs_bits_at(LOGN)) + fbase + bfield(LOGN);
 #pragma unroll
             for (int w = 0; w < W; w++) xw[w] = srcb[w * 32];
         }
@@ -401,17 +426,17 @@ __global__ void __launch_bounds__(32) list_decode_kernel(const ListArgs a)
 // ---------------------------------------------------------------- dispatch
 template <typename real, int LOGN, int L>
 struct ListDispatch {
-    static constexpr int SMEM_TOP = 7;
-    using C = ListCfg<real, LOGN, L, SMEM_TOP>;
+    static constexpr int SMEM_TOP = 7, BITS_TOP = 9;
+    using C = ListCfg<real, LOGN, L, SMEM_TOP, BITS_TOP>;
     static cudaError_t plan(ListPlan *p)
     {
-        auto kern = list_decode_kernel<real, LOGN, L, SMEM_TOP>;
+        auto kern = list_decode_kernel<real, LOGN, L, SMEM_TOP, BITS_TOP>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
         if (e != cudaSuccess) return e;
         int nb = 0;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 32, C::SMEM);
         if (e != cudaSuccess) return e;
-        p->scratch_per_cta = C::GS_REALS * sizeof(real);
+        p->scratch_per_cta = C::GS_BYTES;
         p->smem = C::SMEM;
         p->ctas_per_sm = nb;
         p->frames_per_cta = C::FPW;
@@ -419,7 +444,7 @@ struct ListDispatch {
     }
     static cudaError_t launch(const ListArgs &a, int grid, cudaStream_t st)
     {
-        list_decode_kernel<real, LOGN, L, SMEM_TOP><<<grid, 32, C::SMEM, st>>>(a);
+        list_decode_kernel<real, LOGN, L, SMEM_TOP, BITS_TOP><<<grid, 32, C::SMEM, st>>>(a);
         return cudaGetLastError();
     }
 };
