@@ -12,8 +12,8 @@
 //    unrolled layers.  Slots that hold no path yet (list filling) carry PM=+inf and are exact copies
 //    of path 0, so they compute finite values and never win a comparison.
 //  * Array formulation: at bit j, t=ctz(j): one g-layer at stage t then f-layers t-1..0; stage s keeps
-//    2^s live LLRs.  Stages 0..2 live in registers (a fully unrolled 4-leaf subtree), stages
-//    3..SMEM_TOP-1 in shared memory, the rest in an L2-resident global scratch, all laid out
+//    2^s live LLRs.  Stages 0..1 live in registers, stages
+//    2..SMEM_TOP-1 in shared memory, the rest in an L2-resident global scratch, all laid out
 //    [idx/4][lane][4] so that a warp's 128-bit accesses are contiguous/conflict-free.
 //  * Lazy copy: every path owns a HOME array per stage and a packed pointer word saying where its
 //    current stage-s data lives.  Stage s is rewritten by all paths at the same bits (multiples of
@@ -22,6 +22,10 @@
 //  * Partial sums are kept as packed bit vectors per stage (B[s], 2^s bits) with the same pointer
 //    scheme; stages 2..5 are registers, 6..BITS_TOP-1 shared memory, the rest global scratch.
 //    The final B[n] is the re-encoded codeword, u_hat = B[n] F^{(x)n}.
+//  * Code size matters: with ~13 single-warp CTAs per SM at unrelated program counters the first version
+//    (64-90 KB of SASS, everything unrolled) spent most issue slots waiting for instruction fetch
+//    (ncu: stall_no_instruction 4.0 per issue, profiles/r1_cascl_v1_summary.txt).  The hot loop is now one
+//    f-layer body, one g-layer body and one leaf body, looped rather than unrolled.
 //  * List pruning: each lane ranks its two candidates against the 2L candidates of its frame with
 //    shuffles.  If all candidates are distinct (checked with one warp reduction) rank < L is exactly
 //    the reference's "PM < med"; otherwise (exact ties, or +inf slots while the list fills) a slow
@@ -42,10 +46,10 @@ struct ListCfg {
     static constexpr int N = 1 << LOGN;
     static constexpr int W = (N + 31) / 32;
     static constexpr int FPW = 32 / L;
-    static constexpr int TOP = (SMEM_TOP < LOGN) ? SMEM_TOP : LOGN;            // LLR stages 3..TOP-1 in smem
+    static constexpr int TOP = (SMEM_TOP < LOGN) ? SMEM_TOP : LOGN;            // LLR stages 2..TOP-1 in smem
     static constexpr int BTOP = (BITS_TOP < LOGN + 1) ? BITS_TOP : LOGN + 1;    // bit stages 6..BTOP-1 in smem
     static constexpr int BLO = (BTOP > 6) ? BTOP : 6;                           // first bit stage in global scratch
-    static constexpr int SM_STAGE_REALS = 32 * ((1 << TOP) - 8);
+    static constexpr int SM_STAGE_REALS = 32 * ((1 << TOP) - 4);
     static constexpr int SM_BIT_WORDS = (BTOP > 6) ? 32 * ((1 << (BTOP - 5)) - 2) : 0;
     static constexpr size_t SMEM = (size_t)SM_STAGE_REALS * sizeof(real) + (size_t)SM_BIT_WORDS * 4;
     static constexpr size_t GS_REALS = 32 * (size_t)((1 << LOGN) - (1 << TOP));                    // stages TOP..LOGN-1
@@ -86,7 +90,7 @@ __global__ void __launch_bounds__(32) list_decode_kernel(const ListArgs a)
     const real INF = RT::inf();
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    V4 *const sm_stage = reinterpret_cast<V4 *>(smem_raw);  // stage s (3<=s<TOP): group i4 of lane pl at [8*(2^s-8) + i4*32 + pl]
+    V4 *const sm_stage = reinterpret_cast<V4 *>(smem_raw);  // stage s (2<=s<TOP): group i4 of lane pl at [8*(2^s-4) + i4*32 + pl]
     uint32_t *const sm_bits = reinterpret_cast<uint32_t *>(smem_raw + (size_t)C::SM_STAGE_REALS * sizeof(real));
     unsigned char *const gs_raw = reinterpret_cast<unsigned char *>(a.gscratch) + (size_t)blockIdx.x * C::GS_BYTES;
     V4 *const gs_stage = reinterpret_cast<V4 *>(gs_raw);
@@ -98,11 +102,14 @@ __global__ void __launch_bounds__(32) list_decode_kernel(const ListArgs a)
     const int fl = lane / L;
     const unsigned long long groups = (a.B + FPW - 1) / FPW;
 
-    auto sm_stage_at = [&](int s) -> V4 * { return sm_stage + 8 * ((1 << s) - 8); };
-    auto gs_stage_at = [&](int s) -> V4 * { return gs_stage + 8 * (size_t)((1 << s) - (1 << TOP)); };
+    // home arrays (generic pointers: one code path for shared and global stages keeps the hot loop small)
+    auto stage_at = [&](int s) -> V4 * {
+        return (s < TOP) ? (sm_stage + 8 * ((1 << s) - 4)) : (gs_stage + 8 * (size_t)((1 << s) - (1 << TOP)));
+    };
     // bit array of stage s (s>=6): word w of physical lane pl at [w*32 + pl]
-    auto sm_bits_at = [&](int s) -> uint32_t * { return sm_bits + 32 * ((1 << (s - 5)) - 2); };
-    auto gs_bits_at = [&](int s) -> uint32_t * { return gs_bits + 32 * (size_t)((1 << (s - 5)) - (1 << (BLO - 5))); };
+    auto bits_at = [&](int s) -> uint32_t * {
+        return (s < BTOP) ? (sm_bits + 32 * ((1 << (s - 5)) - 2)) : (gs_bits + 32 * (size_t)((1 << (s - 5)) - (1 << (BLO - 5))));
+    };
 
     for (unsigned long long g = blockIdx.x; g < groups; g += gridDim.x) {
         unsigned long long frame = g * FPW + fl;
@@ -110,101 +117,49 @@ __global__ void __launch_bounds__(32) list_decode_kernel(const ListArgs a)
         if (!valid) frame = a.B - 1;  // tail lanes decode a duplicate and write nothing
         const V4 *const ch4 = reinterpret_cast<const V4 *>(reinterpret_cast<const real *>(a.llr) + frame * (size_t)N);
 
-        real s2[4] = {0, 0, 0, 0}, s1[2] = {0, 0}, pm;
-        ptr_t ptr = 0, bptr = 0;  // fields: LLR stage s at (s-3)*PWID / bit stage s at (s-6)*PWID
+        real s1[2] = {0, 0}, pm;
+        ptr_t ptr = 0, bptr = 0;  // fields: LLR stage s at (s-2)*PWID / bit stage s at (s-6)*PWID
         uint32_t Blow = 0, B5 = 0, ug = 0, flags = 0;
         pm = (k == 0 || L == 1) ? (real)0 : INF;
 
-        auto pfield = [&](int s) -> int { return (L == 1) ? 0 : (int)((ptr >> ((s - 3) * PWID)) & PMASK); };
+        auto pfield = [&](int s) -> int { return (L == 1) ? 0 : (int)((ptr >> ((s - 2) * PWID)) & PMASK); };
         auto bfield = [&](int s) -> int { return (L == 1) ? 0 : (int)((bptr >> ((s - 6) * PWID)) & PMASK); };
         auto set_pfield = [&](int s) {
-            if (L > 1) ptr = (ptr & ~(PMASK << ((s - 3) * PWID))) | ((ptr_t)k << ((s - 3) * PWID));
+            if (L > 1) ptr = (ptr & ~(PMASK << ((s - 2) * PWID))) | ((ptr_t)k << ((s - 2) * PWID));
         };
         auto set_bfield = [&](int s) {
             if (L > 1) bptr = (bptr & ~(PMASK << ((s - 6) * PWID))) | ((ptr_t)k << ((s - 6) * PWID));
         };
 
-        // ---- f-layer producing stage s (3 <= s < LOGN) from stage s+1, into the HOME array ----------------
+        // ---- f-layer producing stage s (2 <= s < LOGN) from stage s+1, into the HOME array -----------------
         auto f_layer = [&](int s) {
             const int cnt4 = 1 << (s - 2);
-            if (s < TOP) {
-                V4 *dst = sm_stage_at(s) + lane;
-                if (s + 1 == LOGN) {
-#pragma unroll 2
-                    for (int i4 = 0; i4 < cnt4; i4++) dst[i4 * 32] = f4<real>(ch4[i4], ch4[i4 + cnt4]);
-                } else if (s + 1 < TOP) {
-                    const V4 *src = sm_stage_at(s + 1) + fbase + pfield(s + 1);
-#pragma unroll 2
-                    for (int i4 = 0; i4 < cnt4; i4++) dst[i4 * 32] = f4<real>(src[i4 * 32], src[(i4 + cnt4) * 32]);
-                } else {
-                    const V4 *src = gs_stage_at(s + 1) + fbase + pfield(s + 1);
-#pragma unroll 2
-                    for (int i4 = 0; i4 < cnt4; i4++) dst[i4 * 32] = f4<real>(src[i4 * 32], src[(i4 + cnt4) * 32]);
-                }
-            } else {
-                V4 *dst = gs_stage_at(s) + lane;
-                if (s + 1 == LOGN) {
-#pragma unroll 2
-                    for (int i4 = 0; i4 < cnt4; i4++) dst[i4 * 32] = f4<real>(ch4[i4], ch4[i4 + cnt4]);
-                } else {
-                    const V4 *src = gs_stage_at(s + 1) + fbase + pfield(s + 1);
-#pragma unroll 2
-                    for (int i4 = 0; i4 < cnt4; i4++) dst[i4 * 32] = f4<real>(src[i4 * 32], src[(i4 + cnt4) * 32]);
-                }
-            }
+            V4 *dst = stage_at(s) + lane;
+            const V4 *src = ch4;
+            int stride = 1;
+            if (s + 1 != LOGN) { src = stage_at(s + 1) + fbase + pfield(s + 1); stride = 32; }
+#pragma unroll 1
+            for (int i4 = 0; i4 < cnt4; i4++) dst[i4 * 32] = f4<real>(src[i4 * stride], src[(i4 + cnt4) * stride]);
             set_pfield(s);
             __syncwarp();
         };
 
-        // ---- g-layer producing stage t (3 <= t < LOGN) from stage t+1 and the partial sums B[t] ------------
-        // `word(w)` returns partial-sum bits 32w..32w+31 of B[t]
-        auto g_run = [&](int t, const V4 *src, int sstride, V4 *dst, auto word) {
-            const int cnt4 = 1 << (t - 2);
-            if (cnt4 >= 8) {
-                for (int w = 0; w < (cnt4 >> 3); w++) {
-                    const uint32_t bw = word(w);
-#pragma unroll 2
-                    for (int q = 0; q < 8; q++) {
-                        const int i4 = w * 8 + q;
-                        dst[i4 * 32] = g4<real>(src[i4 * sstride], src[(i4 + cnt4) * sstride], (bw >> (4 * q)) & 0xFu);
-                    }
-                }
-            } else {
-                const uint32_t bw = word(0);
-                for (int i4 = 0; i4 < cnt4; i4++)
-                    dst[i4 * 32] = g4<real>(src[i4 * sstride], src[(i4 + cnt4) * sstride], (bw >> (4 * i4)) & 0xFu);
-            }
-        };
+        // ---- g-layer producing stage t (2 <= t < LOGN) from stage t+1 and the partial sums B[t] ------------
         auto g_layer = [&](int t) {
-            auto word = [&](int w) -> uint32_t {
-                if (t == 3) return (Blow >> 4) & 0xFFu;
-                if (t == 4) return (Blow >> 12) & 0xFFFFu;
-                if (t == 5) return B5;
-                if (t < BTOP) return sm_bits_at(t)[w * 32 + fbase + bfield(t)];
-                return gs_bits_at(t)[w * 32 + fbase + bfield(t)];
-            };
-            if (t < TOP) {
-                V4 *dst = sm_stage_at(t) + lane;
-                if (t + 1 == LOGN) g_run(t, ch4, 1, dst, word);
-                else if (t + 1 < TOP) g_run(t, sm_stage_at(t + 1) + fbase + pfield(t + 1), 32, dst, word);
-                else g_run(t, gs_stage_at(t + 1) + fbase + pfield(t + 1), 32, dst, word);
-            } else {
-                V4 *dst = gs_stage_at(t) + lane;
-                if (t + 1 == LOGN) g_run(t, ch4, 1, dst, word);
-                else g_run(t, gs_stage_at(t + 1) + fbase + pfield(t + 1), 32, dst, word);
+            const int cnt4 = 1 << (t - 2);
+            V4 *dst = stage_at(t) + lane;
+            const V4 *src = ch4;
+            int stride = 1;
+            if (t + 1 != LOGN) { src = stage_at(t + 1) + fbase + pfield(t + 1); stride = 32; }
+            const uint32_t *bsrc = (t >= 6) ? (bits_at(t) + fbase + bfield(t)) : nullptr;
+            uint32_t bw = (t == 2) ? (Blow & 0xFu) : (t == 3) ? ((Blow >> 4) & 0xFFu) : (t == 4) ? ((Blow >> 12) & 0xFFFFu) : B5;
+#pragma unroll 1
+            for (int i4 = 0; i4 < cnt4; i4++) {
+                if (t >= 6 && (i4 & 7) == 0) bw = bsrc[(i4 >> 3) * 32];
+                dst[i4 * 32] = g4<real>(src[i4 * stride], src[(i4 + cnt4) * stride], (bw >> (4 * (i4 & 7))) & 0xFu);
             }
             set_pfield(t);
             __syncwarp();
-        };
-
-        // stage 3 -> registers (stage 2)
-        auto stage2_from3 = [&](bool is_g) {
-            V4 up, lo;
-            if (3 < TOP) { const V4 *src = sm_stage_at(3) + fbase + pfield(3); up = src[0]; lo = src[32]; }
-            else { const V4 *src = gs_stage_at(3) + fbase + pfield(3); up = src[0]; lo = src[32]; }
-            const V4 o = is_g ? g4<real>(up, lo, Blow & 0xFu) : f4<real>(up, lo);
-#pragma unroll
-            for (int e = 0; e < 4; e++) s2[e] = o.v[e];
         };
 
         // ---- one leaf: frozen -> PM only; information -> decide (SC) or fork/prune (list) ------------------
@@ -238,7 +193,7 @@ __global__ void __launch_bounds__(32) list_decode_kernel(const ListArgs a)
                 const bool f0 = c0 < INF, f1 = c1 < INF;
                 const real d0 = f0 ? c0 : INF, d1 = f1 ? c1 : INF;
                 int r0 = 0, r1 = 0, le0 = 0, le1 = 0;
-#pragma unroll
+#pragma unroll 1
                 for (int i = 0; i < L; i++) {
                     const real v0 = __shfl_sync(0xffffffffu, d0, i, L);
                     const real v1 = __shfl_sync(0xffffffffu, d1, i, L);
@@ -264,8 +219,6 @@ __global__ void __launch_bounds__(32) list_decode_kernel(const ListArgs a)
                 if (td < __popc(both)) src = (int)__fns(both, 0, td + 1);
             }
             const real pc1 = __shfl_sync(0xffffffffu, c1, src);
-#pragma unroll
-            for (int e = 0; e < 4; e++) s2[e] = __shfl_sync(0xffffffffu, s2[e], src);
             s1[0] = __shfl_sync(0xffffffffu, s1[0], src);
             s1[1] = __shfl_sync(0xffffffffu, s1[1], src);
             ptr = __shfl_sync(0xffffffffu, ptr, src);
@@ -282,38 +235,36 @@ __global__ void __launch_bounds__(32) list_decode_kernel(const ListArgs a)
         };
 
         // =================================================================== the N/4 leaf groups
+#pragma unroll 1
         for (int j4 = 0; j4 < N / 4; j4++) {
-            if (j4 == 0) {
-                for (int s = LOGN - 1; s >= 3; s--) f_layer(s);
-                stage2_from3(false);
-            } else {
-                const int t = __ffs(j4) - 1 + 2;
-                if (t == 2) {
-                    stage2_from3(true);
-                } else {
-                    g_layer(t);
-                    for (int s = t - 1; s >= 3; s--) f_layer(s);
-                    stage2_from3(false);
-                }
+            int s = LOGN - 1;
+            if (j4 != 0) {
+                s = __ffs(j4) - 1 + 2;
+                g_layer(s);
+                s--;
             }
-            const int j = 4 * j4;
+#pragma unroll 1
+            for (; s >= 2; s--) f_layer(s);
             ug = 0;
-            // leaf 0: f at stages 1, 0
-            s1[0] = chk<real>(s2[0], s2[2]);
-            s1[1] = chk<real>(s2[1], s2[3]);
-            uint32_t u = leaf(j, chk<real>(s1[0], s1[1]));
-            ug |= u;
-            // leaf 1: g at stage 0
-            u = leaf(j + 1, s1[1] + RT::flip(s1[0], ug & 1u));
-            ug |= u << 1;
-            // leaf 2: g at stage 1 (partial sums u0^u1, u1), f at stage 0
-            s1[0] = s2[2] + RT::flip(s2[0], (ug ^ (ug >> 1)) & 1u);
-            s1[1] = s2[3] + RT::flip(s2[1], (ug >> 1) & 1u);
-            u = leaf(j + 2, chk<real>(s1[0], s1[1]));
-            ug |= u << 2;
-            // leaf 3: g at stage 0
-            u = leaf(j + 3, s1[1] + RT::flip(s1[0], (ug >> 2) & 1u));
-            ug |= u << 3;
+#pragma unroll 1
+            for (int i = 0; i < 4; i++) {
+                real lam;
+                if (!(i & 1)) {
+                    const V4 v = stage_at(2)[fbase + pfield(2)];
+                    if (i == 0) {  // f at stage 1
+                        s1[0] = chk<real>(v.v[0], v.v[2]);
+                        s1[1] = chk<real>(v.v[1], v.v[3]);
+                    } else {       // g at stage 1, partial sums (u0^u1, u1)
+                        s1[0] = v.v[2] + RT::flip(v.v[0], (ug ^ (ug >> 1)) & 1u);
+                        s1[1] = v.v[3] + RT::flip(v.v[1], (ug >> 1) & 1u);
+                    }
+                    lam = chk<real>(s1[0], s1[1]);                              // f at stage 0
+                } else {
+                    lam = s1[1] + RT::flip(s1[0], (ug >> (i - 1)) & 1u);        // g at stage 0
+                }
+                const uint32_t u = leaf(4 * j4 + i, lam);
+                ug |= u << i;
+            }
 
             // ---- partial sums of the finished 4-block, pushed up while the block closes larger blocks -------
             const uint32_t u0 = ug & 1u, u1 = (ug >> 1) & 1u, u2b = (ug >> 2) & 1u, u3 = (ug >> 3) & 1u;
@@ -329,12 +280,14 @@ __global__ void __launch_bounds__(32) list_decode_kernel(const ListArgs a)
             else if (T == 4) Blow = (Blow & ~0xFFFF000u) | (t32 << 12);
             else if (T == 5) B5 = t32;
             else {
-                uint32_t *dst = ((T < BTOP) ? sm_bits_at(T) : gs_bits_at(T)) + lane;
+                uint32_t *dst = bits_at(T) + lane;
                 dst[0] = B5 ^ t32;
                 dst[32] = t32;
-                for (int s = 6; s < T; s++) {
-                    const int len = 1 << (s - 5);
-                    const uint32_t *srcb = ((s < BTOP) ? sm_bits_at(s) : gs_bits_at(s)) + fbase + bfield(s);
+#pragma unroll 1
+                for (int sb = 6; sb < T; sb++) {
+                    const int len = 1 << (sb - 5);
+                    const uint32_t *srcb = bits_at(sb) + fbase + bfield(sb);
+#pragma unroll 1
                     for (int i = 0; i < len; i++) {
                         const uint32_t d = dst[i * 32];
                         dst[(i + len) * 32] = d;
@@ -352,7 +305,7 @@ __global__ void __launch_bounds__(32) list_decode_kernel(const ListArgs a)
         if (LOGN == 5) {
             xw[0] = B5;
         } else {
-            const uint32_t *srcb = ((LOGN < BTOP) ? sm_bits_at(LOGN) : gs_bits_at(LOGN)) + fbase + bfield(LOGN);
+            const uint32_t *srcb = bits_at(LOGN) + fbase + bfield(LOGN);
 #pragma unroll
             for (int w = 0; w < W; w++) xw[w] = srcb[w * 32];
         }
@@ -369,6 +322,7 @@ __global__ void __launch_bounds__(32) list_decode_kernel(const ListArgs a)
             bool pass = false;
             if (a.use_crc) {  // CRcheck: remainder of the I[]-ordered word modulo g(D), as r parity masks
                 uint32_t syn = 0;
+#pragma unroll 1
                 for (int b = 0; b < a.r; b++) {
                     uint32_t acc = 0;
 #pragma unroll
