@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpolargpu.so")
+LIB_PATH = os.environ.get("POLARGPU_LIB") or os.path.join(HERE, "libpolargpu.so")  # override: development A/B builds only
 
 PROGRAMS = ["SC_128", "SC_1024", "SC_128_fag", "SCL_128", "SCL_1024", "SCL_128_fag", "CASCL_128", "CASCL_1024_L8",
             "CASCL_1024_sys", "BP_128", "BP_1024", "BP_128_fag", "BPr_128"]

@@ -362,6 +362,11 @@ static int run_decode(pg_ctx *ctx, const void *d_llr, size_t B, const uint32_t *
         a.gscratch = ctx->d_scratch;
         a.crc_masks = ctx->d_crc_masks;
         a.B = B; a.r = p.crc_bits; a.use_crc = (p.decoder == PG_DEC_CASCL);
+        {
+            int first = p.N;
+            for (int j = 0; j < p.N; j++) if (ctx->inI[j]) { first = j; break; }
+            a.coop_groups = getenv("POLARGPU_NO_COOP") ? 0 : first / 4;
+        }
         a.m = ctx->masks;
         const size_t fpw = 32 / (size_t)p.list_size;
         const size_t groups = (B + fpw - 1) / fpw;

@@ -48,6 +48,7 @@ struct ListArgs {
     const uint32_t *crc_masks;       // [r][N/32] u-domain syndrome masks
     unsigned long long B;
     int r, use_crc;
+    int coop_groups;                 // 4-bit groups before the first non-frozen bit: all paths of a frame are still identical
     CodeMasks m;
 };
 // returns scratch bytes one CTA needs / smem bytes / max resident CTAs per SM for a configuration, or <0 if not compiled

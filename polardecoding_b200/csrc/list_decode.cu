@@ -57,6 +57,31 @@ struct ListCfg {
     static constexpr size_t GS_BYTES = GS_REALS * sizeof(real) + GS_BIT_WORDS * 4;
 };
 
+// explicit 128-bit accesses (the compiler otherwise splits some of these into scalar loads)
+__device__ __forceinline__ vec4<float> ldv(const vec4<float> *p)
+{
+    const float4 t = *reinterpret_cast<const float4 *>(p);
+    vec4<float> o; o.v[0] = t.x; o.v[1] = t.y; o.v[2] = t.z; o.v[3] = t.w;
+    return o;
+}
+__device__ __forceinline__ vec4<double> ldv(const vec4<double> *p)
+{
+    const double2 t = reinterpret_cast<const double2 *>(p)[0], u = reinterpret_cast<const double2 *>(p)[1];
+    vec4<double> o; o.v[0] = t.x; o.v[1] = t.y; o.v[2] = u.x; o.v[3] = u.y;
+    return o;
+}
+__device__ __forceinline__ void stv(vec4<float> *p, const vec4<float> &o)
+{
+    *reinterpret_cast<float4 *>(p) = make_float4(o.v[0], o.v[1], o.v[2], o.v[3]);
+}
+__device__ __forceinline__ void stv(vec4<double> *p, const vec4<double> &o)
+{
+    reinterpret_cast<double2 *>(p)[0] = make_double2(o.v[0], o.v[1]);
+    reinterpret_cast<double2 *>(p)[1] = make_double2(o.v[2], o.v[3]);
+}
+__device__ __forceinline__ float rmax(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double rmax(double a, double b) { return fmax(a, b); }
+
 // one CHK / g evaluation of four neighbouring nodes
 template <typename real>
 __device__ __forceinline__ vec4<real> f4(const vec4<real> &x, const vec4<real> &y)
@@ -117,7 +142,7 @@ __global__ void __launch_bounds__(32) list_decode_kernel(const ListArgs a)
         if (!valid) frame = a.B - 1;  // tail lanes decode a duplicate and write nothing
         const V4 *const ch4 = reinterpret_cast<const V4 *>(reinterpret_cast<const real *>(a.llr) + frame * (size_t)N);
 
-        real s1[2] = {0, 0}, pm;
+        real s2[4] = {0, 0, 0, 0}, s1[2] = {0, 0}, pm;
         ptr_t ptr = 0, bptr = 0;  // fields: LLR stage s at (s-2)*PWID / bit stage s at (s-6)*PWID
         uint32_t Blow = 0, B5 = 0, ug = 0, flags = 0;
         pm = (k == 0 || L == 1) ? (real)0 : INF;
@@ -132,31 +157,69 @@ __global__ void __launch_bounds__(32) list_decode_kernel(const ListArgs a)
         };
 
         // ---- f-layer producing stage s (2 <= s < LOGN) from stage s+1, into the HOME array -----------------
-        auto f_layer = [&](int s) {
+        auto f_layer = [&](int s, bool coop) {
             const int cnt4 = 1 << (s - 2);
-            V4 *dst = stage_at(s) + lane;
-            const V4 *src = ch4;
-            int stride = 1;
-            if (s + 1 != LOGN) { src = stage_at(s + 1) + fbase + pfield(s + 1); stride = 32; }
+            if (coop) {
+                // all lanes of the frame still hold the same path (no information bit yet): they split the layer and
+                // write ONE array, slot 0's home; every pointer field still says slot 0
+                V4 *dst = stage_at(s) + fbase;
+                const V4 *src = ch4;
+                int stride = 1;
+                if (s + 1 != LOGN) { src = stage_at(s + 1) + fbase; stride = 32; }
 #pragma unroll 1
-            for (int i4 = 0; i4 < cnt4; i4++) dst[i4 * 32] = f4<real>(src[i4 * stride], src[(i4 + cnt4) * stride]);
+                for (int i4 = k; i4 < cnt4; i4 += L) stv(dst + i4 * 32, f4<real>(ldv(src + i4 * stride), ldv(src + (i4 + cnt4) * stride)));
+                __syncwarp();
+                return;
+            }
+            if (s + 1 < TOP) {  // shared -> shared (LDS/STS, 32-bit addressing)
+                V4 *dst = sm_stage + 8 * ((1 << s) - 4) + lane;
+                const V4 *src = sm_stage + 8 * ((2 << s) - 4) + fbase + pfield(s + 1);
+                const V4 *src2 = src + cnt4 * 32;
+#pragma unroll 1
+                for (int i4 = 0; i4 < cnt4; i4++, dst += 32, src += 32, src2 += 32) stv(dst, f4<real>(ldv(src), ldv(src2)));
+            } else {
+                V4 *dst = stage_at(s) + lane;
+                const V4 *src = ch4;
+                int stride = 1;
+                if (s + 1 != LOGN) { src = stage_at(s + 1) + fbase + pfield(s + 1); stride = 32; }
+                const V4 *src2 = src + cnt4 * stride;
+#pragma unroll 1
+                for (int i4 = 0; i4 < cnt4; i4++, dst += 32, src += stride, src2 += stride) stv(dst, f4<real>(ldv(src), ldv(src2)));
+            }
             set_pfield(s);
             __syncwarp();
         };
 
         // ---- g-layer producing stage t (2 <= t < LOGN) from stage t+1 and the partial sums B[t] ------------
-        auto g_layer = [&](int t) {
+        auto g_layer = [&](int t, bool coop) {
             const int cnt4 = 1 << (t - 2);
+            if (coop) {  // as above; the partial sums of an all-frozen prefix are zero, so g = lower + upper
+                V4 *dst = stage_at(t) + fbase;
+                const V4 *src = ch4;
+                int stride = 1;
+                if (t + 1 != LOGN) { src = stage_at(t + 1) + fbase; stride = 32; }
+#pragma unroll 1
+                for (int i4 = k; i4 < cnt4; i4 += L) stv(dst + i4 * 32, g4<real>(ldv(src + i4 * stride), ldv(src + (i4 + cnt4) * stride), 0u));
+                __syncwarp();
+                return;
+            }
             V4 *dst = stage_at(t) + lane;
             const V4 *src = ch4;
             int stride = 1;
             if (t + 1 != LOGN) { src = stage_at(t + 1) + fbase + pfield(t + 1); stride = 32; }
-            const uint32_t *bsrc = (t >= 6) ? (bits_at(t) + fbase + bfield(t)) : nullptr;
-            uint32_t bw = (t == 2) ? (Blow & 0xFu) : (t == 3) ? ((Blow >> 4) & 0xFFu) : (t == 4) ? ((Blow >> 12) & 0xFFFFu) : B5;
+            const V4 *src2 = src + cnt4 * stride;
+            if (t < 6) {
+                uint32_t bw = (t == 2) ? (Blow & 0xFu) : (t == 3) ? ((Blow >> 4) & 0xFFu) : (t == 4) ? ((Blow >> 12) & 0xFFFFu) : B5;
 #pragma unroll 1
-            for (int i4 = 0; i4 < cnt4; i4++) {
-                if (t >= 6 && (i4 & 7) == 0) bw = bsrc[(i4 >> 3) * 32];
-                dst[i4 * 32] = g4<real>(src[i4 * stride], src[(i4 + cnt4) * stride], (bw >> (4 * (i4 & 7))) & 0xFu);
+                for (int i4 = 0; i4 < cnt4; i4++, dst += 32, src += stride, src2 += stride, bw >>= 4) stv(dst, g4<real>(ldv(src), ldv(src2), bw & 0xFu));
+            } else {
+                const uint32_t *bsrc = bits_at(t) + fbase + bfield(t);
+#pragma unroll 1
+                for (int w = 0; w < (cnt4 >> 3); w++, bsrc += 32) {
+                    uint32_t bw = *bsrc;
+#pragma unroll 2
+                    for (int q = 0; q < 8; q++, dst += 32, src += stride, src2 += stride, bw >>= 4) stv(dst, g4<real>(ldv(src), ldv(src2), bw & 0xFu));
+                }
             }
             set_pfield(t);
             __syncwarp();
@@ -176,19 +239,32 @@ __global__ void __launch_bounds__(32) list_decode_kernel(const ListArgs a)
             }
             const real c0 = pm + ((lam < (real)0) ? pen : t);
             const real c1 = pm + ((lam > (real)0) ? pen : t);
-            int n0 = 0, n1 = 0;
+            // The reference keeps the candidates with PM < med, med = (L+1)-th smallest of the 2L (SCL_1024.c:619-633).
+            // med without ranking: sort the bit-0 candidates and the bit-1 candidates across the frame's lanes (bitonic
+            // networks on shuffles), then lo_k = min(a_k, b_{L-1-k}) are the L smallest, so sorted[L-1] = max lo, med = min hi.
+            real sa = c0, sb = c1;
 #pragma unroll
-            for (int i = 0; i < L; i++) {
-                const real v0 = __shfl_sync(0xffffffffu, c0, i, L);
-                const real v1 = __shfl_sync(0xffffffffu, c1, i, L);
-                n0 += (int)(v0 < c0) + (int)(v1 < c0);
-                n1 += (int)(v0 < c1) + (int)(v1 < c1);
+            for (int size = 2; size <= L; size <<= 1) {
+#pragma unroll
+                for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                    const real oa = __shfl_xor_sync(0xffffffffu, sa, stride);
+                    const real ob = __shfl_xor_sync(0xffffffffu, sb, stride);
+                    const bool keep_min = (((k & size) == 0) || size == L) == ((k & stride) == 0);
+                    sa = keep_min ? rmin(sa, oa) : rmax(sa, oa);
+                    sb = keep_min ? rmin(sb, ob) : rmax(sb, ob);
+                }
+            }
+            const real rb = __shfl_sync(0xffffffffu, sb, (L - 1 - k), L);
+            real lo = rmin(sa, rb), hi = rmax(sa, rb);
+#pragma unroll
+            for (int d = 1; d < L; d <<= 1) {
+                lo = rmax(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+                hi = rmin(hi, __shfl_xor_sync(0xffffffffu, hi, d));
             }
             bool k0, k1;  // candidate survives
-            const int tot = __reduce_add_sync(0xffffffffu, n0 + n1);
-            if (tot == 32 * (2 * L - 1)) {  // all 2L candidates of every frame distinct and finite
-                k0 = n0 < L;
-                k1 = n1 < L;
+            if (__all_sync(0xffffffffu, lo < hi)) {  // no tie across the list boundary in any frame of the warp (lo finite)
+                k0 = c0 < hi;
+                k1 = c1 < hi;
             } else {
                 const bool f0 = c0 < INF, f1 = c1 < INF;
                 const real d0 = f0 ? c0 : INF, d1 = f1 ? c1 : INF;
@@ -219,6 +295,8 @@ __global__ void __launch_bounds__(32) list_decode_kernel(const ListArgs a)
                 if (td < __popc(both)) src = (int)__fns(both, 0, td + 1);
             }
             const real pc1 = __shfl_sync(0xffffffffu, c1, src);
+#pragma unroll
+            for (int e = 0; e < 4; e++) s2[e] = __shfl_sync(0xffffffffu, s2[e], src);
             s1[0] = __shfl_sync(0xffffffffu, s1[0], src);
             s1[1] = __shfl_sync(0xffffffffu, s1[1], src);
             ptr = __shfl_sync(0xffffffffu, ptr, src);
@@ -237,26 +315,31 @@ __global__ void __launch_bounds__(32) list_decode_kernel(const ListArgs a)
         // =================================================================== the N/4 leaf groups
 #pragma unroll 1
         for (int j4 = 0; j4 < N / 4; j4++) {
+            const bool coop = (L > 1) && (j4 < a.coop_groups);
             int s = LOGN - 1;
             if (j4 != 0) {
                 s = __ffs(j4) - 1 + 2;
-                g_layer(s);
+                g_layer(s, coop);
                 s--;
             }
 #pragma unroll 1
-            for (; s >= 2; s--) f_layer(s);
+            for (; s >= 2; s--) f_layer(s, coop);
             ug = 0;
+            {   // stage 2 of this 4-block (home array, or slot 0's while the lanes cooperate); kept in registers, cloned by shuffle
+                const V4 v = ldv(stage_at(2) + fbase + pfield(2));
+#pragma unroll
+                for (int e = 0; e < 4; e++) s2[e] = v.v[e];
+            }
 #pragma unroll 1
             for (int i = 0; i < 4; i++) {
                 real lam;
                 if (!(i & 1)) {
-                    const V4 v = stage_at(2)[fbase + pfield(2)];
                     if (i == 0) {  // f at stage 1
-                        s1[0] = chk<real>(v.v[0], v.v[2]);
-                        s1[1] = chk<real>(v.v[1], v.v[3]);
+                        s1[0] = chk<real>(s2[0], s2[2]);
+                        s1[1] = chk<real>(s2[1], s2[3]);
                     } else {       // g at stage 1, partial sums (u0^u1, u1)
-                        s1[0] = v.v[2] + RT::flip(v.v[0], (ug ^ (ug >> 1)) & 1u);
-                        s1[1] = v.v[3] + RT::flip(v.v[1], (ug >> 1) & 1u);
+                        s1[0] = s2[2] + RT::flip(s2[0], (ug ^ (ug >> 1)) & 1u);
+                        s1[1] = s2[3] + RT::flip(s2[1], (ug >> 1) & 1u);
                     }
                     lam = chk<real>(s1[0], s1[1]);                              // f at stage 0
                 } else {
@@ -380,7 +463,13 @@ __global__ void __launch_bounds__(32) list_decode_kernel(const ListArgs a)
 // ---------------------------------------------------------------- dispatch
 template <typename real, int LOGN, int L>
 struct ListDispatch {
-    static constexpr int SMEM_TOP = 7, BITS_TOP = 9;
+#ifndef POLAR_SMEM_TOP
+#define POLAR_SMEM_TOP 6
+#endif
+#ifndef POLAR_BITS_TOP
+#define POLAR_BITS_TOP 8
+#endif
+    static constexpr int SMEM_TOP = POLAR_SMEM_TOP, BITS_TOP = POLAR_BITS_TOP;
     using C = ListCfg<real, LOGN, L, SMEM_TOP, BITS_TOP>;
     static cudaError_t plan(ListPlan *p)
     {
