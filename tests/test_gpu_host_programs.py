@@ -1,0 +1,54 @@
+"""GPU: the drop-in C host programs (polardecoding_b200/host/bin/<prog>).  With --rng ref they build frames with the
+reference's own generator on the host and decode on the GPU; their stdout must then be byte-identical to what the
+unmodified reference program prints (KAT captures in tests/golden/kat.json, taken from the compiled reference)."""
+import json
+import os
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "polardecoding_b200", "host", "bin")
+KAT = json.load(open(os.path.join(ROOT, "tests", "golden", "kat.json")))
+
+
+def run(prog, *args, stdin=None):
+    r = subprocess.run([os.path.join(BIN, prog)] + list(args), stdin=stdin or subprocess.DEVNULL, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    return r.stdout
+
+
+def test_sc128_reproduces_reference_stdout_exactly():
+    out = run("SC_128", "--rng", "ref")
+    assert out == KAT["K1_SC_128"]["stdout"]
+
+
+def test_scl128_reproduces_reference_stdout_exactly():
+    out = run("SCL_128", "--rng", "ref")
+    assert out == KAT["K2_SCL_128"]["stdout"]
+
+
+def test_cascl128_reproduces_reference_stdout():
+    k = KAT["K4_CASCL_128"]
+    out = run("CASCL_128", "--rng", "ref", "--seed", "8392", "--ebn0", "1.0:0.5:2.0")
+    want = "".join(l + "\n" for l in k["stdout"].splitlines()[:4])          # SEED line + 3 points
+    assert out == want
+
+
+def test_cascl1024_kat_k5():
+    out = run("CASCL_1024_L8", "--rng", "ref", "--seed", "1242", "--ble", "100")
+    assert out.splitlines()[0] == "SEED = 1242"
+    assert "L = 8\tbSNR = 1.00\terror block = 100\trun = 246\tBLER = 4065.040650e-4" in out      # myResult_1024/CASCL_L8.dat
+    assert "L = 8\tbSNR = 1.50\terror block = 100\trun = 1381\tBLER = 724.112962e-4" in out
+
+
+def test_stdin_matrix_is_accepted_and_philox_mode_runs():
+    fn = "\n".join(" ".join("1" if (i & j) == j else "0" for j in range(128)) for i in range(128)) + "\n"
+    p = subprocess.run([os.path.join(BIN, "BP_128"), "--ebn0", "2.0", "--ble", "20", "--seed", "3", "--verbose"], input=fn, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    lines = p.stdout.splitlines()
+    assert lines[0] == "SEED = 3" and lines[1].startswith("bSNR = 2.00\terror block = 20\trun = ")
+    assert "Mframes/s" in p.stderr
+    out = run("SC_1024", "--ebn0", "2.0", "--ble", "10", "--real", "f64")
+    assert out.startswith("bSNR = 2.00\terror block = 10\trun = ")
