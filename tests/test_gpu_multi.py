@@ -1,0 +1,32 @@
+"""GPU (needs >= 2 devices, skipped otherwise): partitioning the frame space over ranks must not change the result.
+Counter-based Philox keyed by the global frame index makes the multi-GPU run reproduce the single-GPU counters exactly."""
+import os
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "polardecoding_b200", "host", "bin")
+
+
+def ngpus():
+    try:
+        out = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True).stdout
+        return sum(1 for l in out.splitlines() if l.startswith("GPU "))
+    except OSError:
+        return 0
+
+
+@pytest.mark.parametrize("prog,args", [("CASCL_128", ["--ebn0", "1.5:0.5:2.5", "--ble", "150"]), ("BP_128", ["--ebn0", "2.0", "--ble", "60"]),
+                                       ("CASCL_1024_L8", ["--ebn0", "1.5", "--max-frames", "20000"])])
+def test_multi_gpu_equals_single_gpu(prog, args):
+    n = ngpus()
+    if n < 2:
+        pytest.skip("needs 2 GPUs")
+    outs = []
+    for g in (1, 2) + ((4,) if n >= 4 else ()):
+        r = subprocess.run([os.path.join(BIN, prog), "--seed", "11", "--gpus", str(g)] + args, stdin=subprocess.DEVNULL, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr
+        outs.append(r.stdout)
+    assert all(o == outs[0] for o in outs), outs
