@@ -19,12 +19,14 @@
  *                                   reference's order, so that run/error columns reproduce its captures exactly
  *   --real f32|f64                  arithmetic (default f32 with philox, f64 with ref)
  *   --L n  --iters n  --early-stop  list size / BP sweeps / bit-exact fixed-point stop
- *   --gpus n                        partition the frame space over n GPUs (one host thread + one ctx each, NCCL counters)
+ *   --gpus n                        partition the frame space over n GPUs (one forked process + one ctx per GPU, NCCL counters)
  *   --verbose                       throughput and tie/CRC statistics on stderr (stdout stays drop-in)
  */
 #define _POSIX_C_SOURCE 200809L
 #include <math.h>
-#include <pthread.h>
+#include <poll.h>
+#include <sys/types.h>
+#include <sys/wait.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -100,6 +102,10 @@ static void normal_pair(ranq1 *g, double sd, double *n1, double *n2)
 static void consume_stdin(int N)
 {
     if (isatty(STDIN_FILENO)) return;
+    {   /* nothing waiting on stdin (an idle pipe, a closed descriptor): the matrix is optional here, do not block */
+        struct pollfd pf = {STDIN_FILENO, POLLIN, 0};
+        if (poll(&pf, 1, 0) <= 0 || !(pf.revents & (POLLIN | POLLHUP))) return;
+    }
     long cnt = 0, bad = 0, wrong = 0;
     int v;
     while (cnt < (long)N * N && scanf("%d", &v) == 1) {
@@ -234,20 +240,35 @@ static void ref_point(pg_ctx *ctx, const pg_params *p, double snr, uint64_t ble,
     free(I); free(llr); free(u); free(uh); free(fl); free(after); free(w); free(x);
 }
 
-/* ---- --gpus n: one thread + one context per GPU, the library exchanges counters over NCCL ---- */
-typedef struct { pg_ctx *ctx; double snr; uint64_t first, ble, maxf; pg_counters out; int rc; } worker;
-static void *worker_main(void *arg)
+/* ---- --gpus n: one PROCESS per GPU (fork before any CUDA call); rank 0 creates the NCCL id and hands it to the
+ * others through pipes; every rank makes the same pg_simulate calls, the library exchanges the counters, rank 0 prints ---- */
+static int spawn_ranks(long gpus, unsigned char id[128], int *have_id)
 {
-    worker *w = (worker *)arg;
-    w->rc = pg_simulate(w->ctx, w->snr, w->first, w->ble, w->maxf, 1, &w->out);
-    return NULL;
-}
-typedef struct { pg_ctx *ctx; const void *id; int rc; } comm_job;
-static void *comm_main(void *arg)
-{
-    comm_job *j = (comm_job *)arg;
-    j->rc = pg_comm_init(j->ctx, j->id);
-    return NULL;
+    int (*fds)[2] = (int (*)[2])malloc(sizeof(int[2]) * (size_t)gpus);
+    for (long g = 1; g < gpus; g++)
+        if (pipe(fds[g])) { perror("pipe"); exit(3); }
+    int rank = 0;
+    for (long g = 1; g < gpus; g++) {
+        const pid_t pid = fork();
+        if (pid < 0) { perror("fork"); exit(3); }
+        if (pid == 0) { rank = (int)g; break; }
+    }
+    if (rank == 0) {
+        if (pg_comm_unique_id(id)) { fprintf(stderr, "polar_sim: %s\n", pg_last_error(NULL)); exit(3); }
+        for (long g = 1; g < gpus; g++) {
+            close(fds[g][0]);
+            if (write(fds[g][1], id, 128) != 128) { perror("write"); exit(3); }
+            close(fds[g][1]);
+        }
+    } else {
+        close(fds[rank][1]);
+        if (read(fds[rank][0], id, 128) != 128) { fprintf(stderr, "polar_sim: rank %d got no NCCL id\n", rank); exit(3); }
+        close(fds[rank][0]);
+        if (!freopen("/dev/null", "w", stdout)) exit(3);   /* only rank 0 prints the result lines */
+    }
+    *have_id = 1;
+    free(fds);
+    return rank;
 }
 
 int main(int argc, char **argv)
@@ -309,20 +330,19 @@ int main(int argc, char **argv)
     else if (pd->seed_mod) printf("SEED = %ld\n", (long)SEED);
     consume_stdin(p.N);
 
-    pg_ctx **ctx = (pg_ctx **)calloc((size_t)gpus, sizeof(pg_ctx *));
-    for (long g = 0; g < gpus; g++) {
-        pg_params q = p;
-        q.device = (int)g; q.rank = (int)g; q.nranks = (int)gpus;
-        if (pg_create(&q, &ctx[g])) { fprintf(stderr, "polar_sim: pg_create (GPU %ld): %s\n", g, pg_last_error(NULL)); return 3; }
-    }
+    fflush(stdout);
+    int rank = 0, have_id = 0;
+    unsigned char id[128];
     if (gpus > 1) {
-        unsigned char id[128];
-        if (pg_comm_unique_id(id)) { fprintf(stderr, "polar_sim: %s\n", pg_last_error(NULL)); return 3; }
-        pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)gpus);
-        comm_job *cj = (comm_job *)malloc(sizeof(comm_job) * (size_t)gpus);
-        for (long g = 0; g < gpus; g++) { cj[g].ctx = ctx[g]; cj[g].id = id; pthread_create(&th[g], NULL, comm_main, &cj[g]); }
-        for (long g = 0; g < gpus; g++) { pthread_join(th[g], NULL); if (cj[g].rc) die("pg_comm_init", ctx[g]); }
-        free(th); free(cj);
+        setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0); /* stdout carries only the reference's result lines */
+        rank = spawn_ranks(gpus, id, &have_id);
+    }
+    pg_ctx *ctx = NULL;
+    {
+        pg_params q = p;
+        q.device = rank; q.rank = rank; q.nranks = (int)gpus;
+        if (pg_create(&q, &ctx)) { fprintf(stderr, "polar_sim: pg_create (GPU %d): %s\n", rank, pg_last_error(NULL)); return 3; }
+        if (have_id && pg_comm_init(ctx, id)) die("pg_comm_init", ctx);
     }
 
     ref_state st;
@@ -334,31 +354,25 @@ int main(int argc, char **argv)
         struct timespec t0, t1;
         clock_gettime(CLOCK_MONOTONIC, &t0);
         if (use_ref) {
-            ref_point(ctx[0], &p, bSNR_dB, (uint64_t)ble, (uint64_t)maxf, &st, &c);
-        } else if (gpus == 1) {
-            if (pg_simulate(ctx[0], bSNR_dB, next_frame, (uint64_t)ble, (uint64_t)maxf, 1, &c)) die("pg_simulate", ctx[0]);
+            ref_point(ctx, &p, bSNR_dB, (uint64_t)ble, (uint64_t)maxf, &st, &c);
         } else {
-            pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)gpus);
-            worker *w = (worker *)calloc((size_t)gpus, sizeof(worker));
-            for (long g = 0; g < gpus; g++) {
-                w[g].ctx = ctx[g]; w[g].snr = bSNR_dB; w[g].first = next_frame; w[g].ble = (uint64_t)ble; w[g].maxf = (uint64_t)maxf;
-                pthread_create(&th[g], NULL, worker_main, &w[g]);
-            }
-            for (long g = 0; g < gpus; g++) { pthread_join(th[g], NULL); if (w[g].rc) die("pg_simulate", ctx[g]); }
-            c = w[0].out;
-            free(th); free(w);
+            if (pg_simulate(ctx, bSNR_dB, next_frame, (uint64_t)ble, (uint64_t)maxf, 1, &c)) die("pg_simulate", ctx);
         }
         clock_gettime(CLOCK_MONOTONIC, &t1);
         next_frame += c.frames;
         print_point(pd, &p, bSNR_dB, &c);
-        if (verbose) {
+        if (verbose && rank == 0) {
             const double s = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
             fprintf(stderr, "# %s Eb/N0 %.2f: %llu frames in %.3f s = %.3f Mframes/s = %.4f Gbit/s info; tie frames %llu, CRC-fail frames %llu, BP sweeps/frame %.2f\n",
                     pd->name, bSNR_dB, (unsigned long long)c.frames, s, (double)c.frames / s / 1e6, (double)c.frames * p.K / s / 1e9,
                     (unsigned long long)c.tie_frames, (unsigned long long)c.crc_fail, c.frames ? (double)c.bp_sweeps / (double)c.frames : 0.0);
         }
     }
-    for (long g = 0; g < gpus; g++) pg_destroy(ctx[g]);
-    free(ctx);
+    pg_destroy(ctx);
+    if (rank == 0 && gpus > 1) {
+        int status = 0, bad = 0;
+        while (wait(&status) > 0) bad |= !(WIFEXITED(status) && WEXITSTATUS(status) == 0);
+        return bad ? 4 : 0;
+    }
     return 0;
 }

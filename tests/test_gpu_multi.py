@@ -26,7 +26,7 @@ def test_multi_gpu_equals_single_gpu(prog, args):
         pytest.skip("needs 2 GPUs")
     outs = []
     for g in (1, 2) + ((4,) if n >= 4 else ()):
-        r = subprocess.run([os.path.join(BIN, prog), "--seed", "11", "--gpus", str(g)] + args, stdin=subprocess.DEVNULL, capture_output=True, text=True, timeout=600)
+        r = subprocess.run([os.path.join(BIN, prog), "--seed", "11", "--gpus", str(g)] + args, stdin=subprocess.DEVNULL, capture_output=True, text=True, timeout=120)
         assert r.returncode == 0, r.stderr
         outs.append(r.stdout)
     assert all(o == outs[0] for o in outs), outs
