@@ -334,7 +334,10 @@ int main(int argc, char **argv)
     int rank = 0, have_id = 0;
     unsigned char id[128];
     if (gpus > 1) {
-        setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0); /* stdout carries only the reference's result lines */
+        {   /* stdout carries only the reference's result lines: keep NCCL's version banner off it */
+            const char *dbg = getenv("NCCL_DEBUG");
+            if (!dbg || !strcmp(dbg, "VERSION") || !strcmp(dbg, "version")) setenv("NCCL_DEBUG", "WARN", 1);
+        }
         rank = spawn_ranks(gpus, id, &have_id);
     }
     pg_ctx *ctx = NULL;
