@@ -336,7 +336,7 @@ int main(int argc, char **argv)
     if (gpus > 1) {
         {   /* stdout carries only the reference's result lines: keep NCCL's version banner off it */
             const char *dbg = getenv("NCCL_DEBUG");
-            if (!dbg || !strcmp(dbg, "VERSION") || !strcmp(dbg, "version")) setenv("NCCL_DEBUG", "WARN", 1);
+            if (!dbg) setenv("NCCL_DEBUG", "NONE", 1); /* VERSION and WARN levels both print the banner to stdout */
         }
         rank = spawn_ranks(gpus, id, &have_id);
     }

@@ -29,4 +29,5 @@ def test_multi_gpu_equals_single_gpu(prog, args):
         r = subprocess.run([os.path.join(BIN, prog), "--seed", "11", "--gpus", str(g)] + args, stdin=subprocess.DEVNULL, capture_output=True, text=True, timeout=120)
         assert r.returncode == 0, r.stderr
         outs.append(r.stdout)
-    assert all(o == outs[0] for o in outs), outs
+    for g, o in enumerate(outs[1:]):
+        assert o == outs[0], "outputs differ:\n--- 1 GPU\n%s\n--- more GPUs (#%d)\n%s" % (outs[0], g, o)
