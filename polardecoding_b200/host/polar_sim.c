@@ -31,6 +31,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <strings.h>
 #include <time.h>
 #include <unistd.h>
 
@@ -336,7 +337,8 @@ int main(int argc, char **argv)
     if (gpus > 1) {
         {   /* stdout carries only the reference's result lines: keep NCCL's version banner off it */
             const char *dbg = getenv("NCCL_DEBUG");
-            if (!dbg) setenv("NCCL_DEBUG", "NONE", 1); /* VERSION and WARN levels both print the banner to stdout */
+            /* the VERSION and WARN levels both print the banner to stdout; INFO/TRACE are the user's explicit choice */
+            if (!dbg || !strcasecmp(dbg, "VERSION") || !strcasecmp(dbg, "WARN")) setenv("NCCL_DEBUG", "NONE", 1);
         }
         rank = spawn_ranks(gpus, id, &have_id);
     }
