@@ -102,6 +102,11 @@ int pg_info_set(const pg_ctx *ctx, int *I_out, uint8_t *inI_out);
 int pg_decode_llr(pg_ctx *ctx, const void *llr, int llr_is_f64, size_t B, uint8_t *u_hat, uint32_t *flags);
 /* as pg_decode_llr, but the decisions come back packed ([B][N/32] words, HOST): 32x less device-to-host traffic */
 int pg_decode_llr_packed(pg_ctx *ctx, const void *llr, int llr_is_f64, size_t B, uint32_t *u_hat_packed, uint32_t *flags);
+/* decode with the truth supplied by the caller -- the shape of BPr(double *y, int *u_hat, int *u) (BPr_128.c:373): u_true is
+ * [B][N] bytes (HOST); wrong counted bits per frame go to frame_err (may be NULL), counters are ADDED to *acc, u_hat may be
+ * NULL.  With pg_bpr_config active and a BP context this also accumulates the BPR statistic. */
+int pg_decode_llr_counted(pg_ctx *ctx, const void *llr, int llr_is_f64, size_t B, const uint8_t *u_true, uint8_t *u_hat,
+                          pg_counters *acc, uint16_t *frame_err);
 /* same with DEVICE pointers and packed output (u_hat_packed: [B][N/32] words); no copies, asynchronous on the ctx stream */
 int pg_decode_llr_device(pg_ctx *ctx, const void *d_llr, int llr_is_f64, size_t B, uint32_t *d_u_hat_packed, uint32_t *d_flags);
 

@@ -54,6 +54,7 @@ def load_library():
     lib.pg_info_set.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_uint8)]
     lib.pg_decode_llr.argtypes = [vp, vp, C.c_int, C.c_size_t, vp, vp]
     lib.pg_decode_llr_packed.argtypes = [vp, vp, C.c_int, C.c_size_t, vp, vp]
+    lib.pg_decode_llr_counted.argtypes = [vp, vp, C.c_int, C.c_size_t, vp, vp, C.POINTER(PgCounters), vp]
     lib.pg_decode_llr_device.argtypes = [vp, vp, C.c_int, C.c_size_t, vp, vp]
     lib.pg_decode_count_device.argtypes = [vp, vp, C.c_int, C.c_size_t, vp, vp, vp]
     lib.pg_counters_read.argtypes = [vp, C.POINTER(PgCounters), C.c_int]
@@ -140,6 +141,21 @@ class Engine:
             rc = self.lib.pg_decode_llr(self.ctx, llr.ctypes.data, int(llr.dtype == np.float64), B, out.ctypes.data, flags.ctypes.data)
         self._check(rc, "pg_decode_llr")
         return out, flags
+
+    def decode_llr_counted(self, llr, u_true, acc=None):
+        """pg_decode_llr_counted: -> (u_hat (B,N) uint8, frame_err (B,) uint16, counters)"""
+        llr = np.ascontiguousarray(llr)
+        if llr.dtype not in (np.float32, np.float64):
+            llr = llr.astype(np.float64)
+        llr = llr.reshape(-1, self.N)
+        B = llr.shape[0]
+        u_true = np.ascontiguousarray(u_true, dtype=np.uint8).reshape(B, self.N)
+        out = np.zeros((B, self.N), dtype=np.uint8)
+        fe = np.zeros(B, dtype=np.uint16)
+        acc = acc if acc is not None else PgCounters()
+        rc = self.lib.pg_decode_llr_counted(self.ctx, llr.ctypes.data, int(llr.dtype == np.float64), B, u_true.ctypes.data, out.ctypes.data, C.byref(acc), fe.ctypes.data)
+        self._check(rc, "pg_decode_llr_counted")
+        return out, fe, acc
 
     def channel(self, ebn0_db, first_frame, B):
         """-> (llr (B,N) float32|float64, u (B,N) uint8) exactly as pg_simulate would feed the decoder."""

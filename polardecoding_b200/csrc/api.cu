@@ -298,6 +298,8 @@ extern "C" int pg_info_set(const pg_ctx *ctx, int *I_out, uint8_t *inI_out)
     return PG_OK;
 }
 
+static void add_counters(pg_counters *acc, const unsigned long long *c);
+
 // ---------------------------------------------------------------- launches
 // POLARGPU_DEBUG=1: synchronise after every kernel so that a fault is attributed to the launch that caused it
 static int debug_sync(pg_ctx *ctx, const char *what)
@@ -451,6 +453,45 @@ static int decode_host(pg_ctx *ctx, const void *llr, int llr_is_f64, size_t B, u
     }
     if (flags)
         for (size_t i = 0; i < B; i++) flags[i] = ((flags[i] >> 16) & 3u) | ((flags[i] >> 24) << 8);
+    return PG_OK;
+}
+
+extern "C" int pg_decode_llr_counted(pg_ctx *ctx, const void *llr, int llr_is_f64, size_t B, const uint8_t *u_true, uint8_t *u_hat,
+                                     pg_counters *acc, uint16_t *frame_err)
+{
+    if (!ctx || !llr || !u_true || !acc) return PG_ERR_ARG;
+    CU(cudaSetDevice(ctx->p.device));
+    const size_t N = ctx->p.N, W = ctx->W;
+    const size_t esz = llr_is_f64 ? 8 : 4;
+    const bool conv = (llr_is_f64 != 0) != ctx->f64;
+    std::vector<uint32_t> packed;
+    for (size_t off = 0; off < B; off += ctx->chunk_max) {
+        const size_t b = std::min(ctx->chunk_max, B - off);
+        int rc = ensure_capacity(ctx, b);
+        if (rc) return rc;
+        packed.assign(b * W, 0u);
+        for (size_t f = 0; f < b; f++)
+            for (size_t j = 0; j < N; j++)
+                if (u_true[(off + f) * N + j]) packed[f * W + (j >> 5)] |= 1u << (j & 31);
+        CU(cudaMemcpyAsync(ctx->d_truth, packed.data(), b * W * 4, cudaMemcpyHostToDevice, ctx->st));
+        void *dst = conv ? ctx->d_in : ctx->d_llr;
+        CU(cudaMemcpyAsync(dst, (const char *)llr + off * N * esz, b * N * esz, cudaMemcpyHostToDevice, ctx->st));
+        if (conv) { CU(launch_convert_llr(ctx->d_in, llr_is_f64 != 0, ctx->d_llr, ctx->f64, b * N, ctx->st)); ctx->launches++; }
+        CU(cudaMemsetAsync(ctx->d_counters, 0, CNT_N * 8, ctx->st));
+        rc = run_decode(ctx, ctx->d_llr, b, ctx->d_truth, ctx->d_uhat, ctx->d_info, true);
+        if (rc) return rc;
+        if (u_hat) {
+            CU(launch_unpack_bits(ctx->d_uhat, ctx->d_bytes, b, (int)N, ctx->st));
+            ctx->launches++;
+            CU(cudaMemcpyAsync(u_hat + off * N, ctx->d_bytes, b * N, cudaMemcpyDeviceToHost, ctx->st));
+        }
+        CU(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, CNT_N * 8, cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaMemcpyAsync(ctx->h_info, ctx->d_info, b * 4, cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaStreamSynchronize(ctx->st));
+        add_counters(acc, ctx->h_counters);
+        if (frame_err)
+            for (size_t i = 0; i < b; i++) frame_err[off + i] = (uint16_t)(ctx->h_info[i] & 0xFFFFu);
+    }
     return PG_OK;
 }
 

@@ -51,6 +51,9 @@ __global__ void __launch_bounds__(THREADS) bp_decode_kernel(const BpArgs a)
     real *Lm = reinterpret_cast<real *>(smem_raw);        // Lm[(s-1)*N + j] = l(s,j), s=1..n-1
     real *Rm = Lm + (size_t)(n - 1) * N;                  // Rm[(s-1)*N + j] = r(s,j), s=1..n-1
     uint32_t *uh = reinterpret_cast<uint32_t *>(smem_raw + C::MSG * sizeof(real));  // W words + [W]=nerr, [W+1]=frame lo, [W+2]=frame hi
+    // BPR statistic (only when a.bpr_ns > 0; the launch then adds N + 8*16*4 bytes): one byte per position, per-CTA counters
+    uint8_t *bb = reinterpret_cast<uint8_t *>(uh + W + 4);
+    uint32_t *bE = reinterpret_cast<uint32_t *>(bb + N);
     const int tid = threadIdx.x;
 
     auto r0 = [&](int j) -> real { return ((a.m.info[j >> 5] >> (j & 31)) & 1u) ? (real)0 : (real)999; };
@@ -75,7 +78,55 @@ __global__ void __launch_bounds__(THREADS) bp_decode_kernel(const BpArgs a)
         }
         for (int i = tid; i < (n - 1) * N; i += THREADS) Lm[i] = (real)0;  // BP_1024.c:378-380
         if (tid < W + 1) uh[tid] = 0;
+        if (a.bpr_ns) for (int i = tid; i < 8 * 16; i += THREADS) bE[i] = 0;
         cta_sync<THREADS>();
+
+        // BPR sample (BPr_128.c:418-442): at every stage i decide on l(i,.)+r(i,.), undo encoder stages i-1..0, count wrong payload bits
+        auto bpr_sample = [&](int q) {
+            const uint32_t *tw = a.truth + frame * (size_t)W;
+            for (int i = 0; i <= n; i++) {
+#pragma unroll
+                for (int e = 0; e < BPT; e++) {
+                    const int qq = tid + e * THREADS;
+                    real su, sl;  // l+r of the two positions this thread owns at stage i
+                    int ju, jl;
+                    if (i == 0) {  // l(0,.) is not state: form it from l(1,.), r(0,.)
+                        ju = 2 * qq; jl = ju + 1;
+                        const real lu = Lm[ju], ll = Lm[jl], ru = r0(ju), rl = r0(jl);
+                        su = chk<real>(lu, ll + rl) + ru;
+                        sl = (ll + chk<real>(ru, lu)) + rl;
+                    } else if (i == n) {  // r(n,.) is not state: form it from r(n-1,.), l(n,.) = channel
+                        ju = qq; jl = qq + N / 2;
+                        const real *rin = Rm + (size_t)(n - 2) * N;
+                        const real ru = (n == 1) ? r0(ju) : rin[ju], rl = (n == 1) ? r0(jl) : rin[jl];
+                        su = ch_up[e] + chk<real>(ru, ch_lo[e] + rl);
+                        sl = ch_lo[e] + (rl + chk<real>(ru, ch_up[e]));
+                    } else {
+                        ju = 2 * qq; jl = ju + 1;
+                        su = Lm[(size_t)(i - 1) * N + ju] + Rm[(size_t)(i - 1) * N + ju];
+                        sl = Lm[(size_t)(i - 1) * N + jl] + Rm[(size_t)(i - 1) * N + jl];
+                    }
+                    bb[ju] = (su >= (real)0) ? 0 : 1;
+                    bb[jl] = (sl >= (real)0) ? 0 : 1;
+                }
+                cta_sync<THREADS>();
+                for (int kk = i; kk > 0; kk--) {  // BPr_128.c:428-437
+                    const int d = 1 << (kk - 1);
+#pragma unroll
+                    for (int e = 0; e < BPT; e++) {
+                        const int qq = tid + e * THREADS;
+                        const int j = ((qq >> (kk - 1)) << kk) | (qq & (d - 1));
+                        bb[j] ^= bb[j + d];
+                    }
+                    cta_sync<THREADS>();
+                }
+                uint32_t wrong = 0;
+                for (int j = tid; j < N; j += THREADS)
+                    if ((a.m.cnt[j >> 5] >> (j & 31)) & 1u) wrong += (uint32_t)(bb[j] != ((__ldg(tw + (j >> 5)) >> (j & 31)) & 1u));
+                if (wrong) atomicAdd(&bE[q * 16 + i], wrong);
+                cta_sync<THREADS>();
+            }
+        };
 
         int sweeps = 0;
         for (int it = 0; it < a.iters; it++) {
@@ -120,10 +171,20 @@ __global__ void __launch_bounds__(THREADS) bp_decode_kernel(const BpArgs a)
                 cta_sync<THREADS>();
             }
             sweeps = it + 1;
+            if (a.bpr_ns && a.truth)
+                for (int q = 0; q < a.bpr_ns; q++)
+                    if (a.bpr_samples[q] == sweeps) bpr_sample(q);
             if (a.early_stop) {
                 const int any = (THREADS == 32) ? __any_sync(0xffffffffu, changed) : __syncthreads_or(changed);
                 if (!any) break;
             }
+        }
+        if (a.bpr_ns && a.truth) {  // samples scheduled after a fixed-point stop see the same, final, state
+            for (int q = 0; q < a.bpr_ns; q++)
+                if (a.bpr_samples[q] > sweeps && a.bpr_samples[q] <= a.iters) bpr_sample(q);
+            cta_sync<THREADS>();
+            for (int i = tid; i < 8 * 16; i += THREADS)
+                if (bE[i]) atomicAdd(a.bpr_E + i, (unsigned long long)bE[i]);
         }
         // ---- l(0,.) from the final state and the decision (BP_1024.c:410-413,417-425)
         {
@@ -185,7 +246,12 @@ struct BpDispatch {
     }
     static cudaError_t launch(const BpArgs &a, int grid, cudaStream_t st)
     {
-        bp_decode_kernel<real, LOGN, THREADS><<<grid, THREADS, C::SMEM, st>>>(a);
+        const size_t smem = C::SMEM + (a.bpr_ns ? (size_t)C::N + 8 * 16 * 4 : 0);
+        if (a.bpr_ns) {
+            cudaError_t e = cudaFuncSetAttribute(bp_decode_kernel<real, LOGN, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        bp_decode_kernel<real, LOGN, THREADS><<<grid, THREADS, smem, st>>>(a);
         return cudaGetLastError();
     }
 };

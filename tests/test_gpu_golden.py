@@ -101,3 +101,28 @@ def test_fer_matches_reference_tables():
         print("%s %.1f dB: BLER %.5f (%d errors / %d frames) reference %.5f" % (prog, ebn0, bler, r.err_blocks, r.frames, ref_bler))
         assert abs(bler - ref_bler) < 2.6 * sd, (prog, bler, ref_bler)
         eng.close()
+
+
+def test_bpr_statistic_matches_reference():
+    """BPr_128.c:418-568: per-stage hard decision + re-encode error counts E[sample][stage], against the compiled
+    reference's E (golden) and against the oracle on fresh frames; also with the fixed-point stop (same statistic)."""
+    from polardecoding_b200 import Engine
+    z, llr, u, uh = load("BPr_128")
+    samples = [int(v) for v in z["samples"]]
+    for early in (0, 1):
+        eng = Engine("BPr_128", real="f64", bp_early_stop=early)
+        eng.bpr_config(samples)
+        got, fe, acc = eng.decode_llr_counted(llr, u)
+        assert (got == uh).all()
+        E = eng.bpr_read()
+        assert (E == z["E"]).all(), (early, E, z["E"])
+        assert acc.frames == len(llr) and (fe == (got != u)[:, eng.I].sum(1)).all()
+        eng.close()
+    o = Oracle("BPr_128")
+    uu, l2 = o.frames_ref_stream(2.0, 40, seed=99)
+    _, Eo = o.bpr(l2, uu, samples)
+    eng = Engine("BPr_128", real="f64")
+    eng.bpr_config(samples)
+    eng.decode_llr_counted(l2, uu)
+    assert (eng.bpr_read() == Eo).all()
+    eng.close()
