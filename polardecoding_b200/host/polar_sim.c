@@ -49,7 +49,7 @@ typedef struct prog_def {
     int fmt;             /* output format id */
 } prog_def;
 
-enum { F_SC, F_SCL_1E1, F_SCL_1E2, F_SCL_FAG, F_CASCL_1E3, F_CASCL_1E4, F_CASCL_SYS, F_BP_128, F_BP_1024 };
+enum { F_SC, F_SCL_1E1, F_SCL_1E2, F_SCL_FAG, F_CASCL_1E3, F_CASCL_1E4, F_CASCL_SYS, F_BP_128, F_BP_1024, F_BPR };
 
 static const prog_def PROGS[] = {
     {"SC_128", 1.0, 4.0, 100, 0, F_SC},           /* SC_128.c:164,169,218-221 */
@@ -64,6 +64,7 @@ static const prog_def PROGS[] = {
     {"BP_128", 1.0, 4.0, 200, 1000, F_BP_128},    /* BP_128.c:96,163,217 */
     {"BP_1024", 1.0, 3.5, 200, 1000, F_BP_1024},  /* BP_1024.c:136,203,255-257 */
     {"BP_128_fag", 1.0, 4.0, 200, 1000, F_BP_128}, /* BP_128_fag.c:98,179 */
+    {"BPr_128", 1.0, 4.0, 200, 1000, F_BPR},      /* BPr_128.c:105,171,227-258 */
 };
 
 static void die(const char *msg, pg_ctx *ctx)
@@ -121,6 +122,9 @@ static void consume_stdin(int N)
         fprintf(stderr, "polar_sim: note: the matrix on stdin is not F^{(x)n}; the GPU encoder uses F^{(x)n} (as every reference run does)\n");
 }
 
+static const int BPR_SAMPLES[6] = {3, 6, 10, 20, 40, 80}; /* i0..i5, BPr_128.c:18-23 */
+static uint64_t g_bprE[6 * 16];                             /* E[sample][stage] of the current Eb/N0 point */
+
 static void print_point(const prog_def *pd, const pg_params *p, double snr, const pg_counters *c)
 {
     const int errBlock = (int)c->err_blocks, run = (int)c->frames, errbit = (int)c->err_bits, K = p->K, L = p->list_size;
@@ -157,6 +161,18 @@ static void print_point(const prog_def *pd, const pg_params *p, double snr, cons
         printf("bSNR = %.2lf\terror block = %d\trun = %d\t", snr, errBlock, run);
         printf("BLER = %lf * 10^-3\n", ((double)errBlock) * 1000 / run);
         break;
+    case F_BPR: { /* BPr_128.c:227-258 */
+        int nst = 0;
+        while ((1 << nst) < p->N) nst++;
+        printf("bSNR = %.2lf\terror block = %d\trun = %d\t", snr, errBlock, run);
+        for (int t = 0; t < 6; t++) {
+            printf(t == 0 ? "\nAfter %2d iterations:\n" : "After %2d iterations:\n", BPR_SAMPLES[t]);
+            for (int i = 0; i <= nst; i++) printf("%lf\t", ((double)g_bprE[t * (nst + 1) + i]) / run);
+            printf("\n");
+        }
+        printf("BLER = %lfe-2\tBER = %lfe-2\tK * BER = %lf\n", ((double)errBlock) * 100 / run, ((double)errbit) * 100 / K / run, ((double)errbit) / run);
+        break;
+    }
     }
     fflush(stdout);
 }
@@ -164,7 +180,7 @@ static void print_point(const prog_def *pd, const pg_params *p, double snr, cons
 /* ---- --rng ref: frames built on the host exactly as the reference's main() does, decoded on the GPU ---- */
 typedef struct { ranq1 g; int m; } ref_state;
 
-static void ref_point(pg_ctx *ctx, const pg_params *p, double snr, uint64_t ble, uint64_t max_frames, ref_state *st, pg_counters *out)
+static void ref_point(pg_ctx *ctx, const pg_params *p, double snr, uint64_t ble, uint64_t max_frames, ref_state *st, pg_counters *out, int bpr)
 {
     const int N = p->N, K = p->K, r = p->crc_bits, nI = K + r;
     int *I = (int *)malloc(sizeof(int) * (size_t)nI);
@@ -225,7 +241,13 @@ static void ref_point(pg_ctx *ctx, const pg_params *p, double snr, uint64_t ble,
             if (st->m >= 63) st->m -= 63;
             after[f] = *st;
         }
-        if (pg_decode_llr(ctx, llr, 1, nb, uh, fl)) die("pg_decode_llr", ctx);
+        if (bpr) { /* BPr(y, u_hat, u): the truth goes in with the frame (BPr_128.c:213) */
+            pg_counters scratch;
+            memset(&scratch, 0, sizeof(scratch));
+            memset(fl, 0, sizeof(uint32_t) * nb);
+            if (pg_bpr_reset(ctx) || pg_decode_llr_counted(ctx, llr, 1, nb, u, uh, &scratch, NULL)) die("pg_decode_llr_counted", ctx);
+        } else if (pg_decode_llr(ctx, llr, 1, nb, uh, fl)) die("pg_decode_llr", ctx);
+        size_t used = nb;
         for (size_t f = 0; f < nb; f++) {
             int bad = 0;
             for (int i = p->count_from; i < nI; i++)
@@ -234,7 +256,15 @@ static void ref_point(pg_ctx *ctx, const pg_params *p, double snr, uint64_t ble,
             out->frames++;
             out->tie_frames += fl[f] & 1u;
             out->crc_fail += (fl[f] >> 1) & 1u;
-            if (ble && out->err_blocks >= ble) { *st = after[f]; done = 1; break; } /* the reference stops here (SC_128.c:169) */
+            if (ble && out->err_blocks >= ble) { *st = after[f]; done = 1; used = f + 1; break; } /* the reference stops here (SC_128.c:169) */
+        }
+        if (bpr) { /* the statistic covers exactly the frames the sequential program would have run */
+            uint64_t E[6 * 16];
+            pg_counters scratch;
+            memset(&scratch, 0, sizeof(scratch));
+            if (used < nb && (pg_bpr_reset(ctx) || pg_decode_llr_counted(ctx, llr, 1, used, u, NULL, &scratch, NULL))) die("pg_decode_llr_counted", ctx);
+            if (pg_bpr_read(ctx, E)) die("pg_bpr_read", ctx);
+            for (int i = 0; i < 6 * 16; i++) g_bprE[i] += E[i];
         }
         if (max_frames && out->frames >= max_frames) done = 1;
     }
@@ -348,6 +378,7 @@ int main(int argc, char **argv)
         q.device = rank; q.rank = rank; q.nranks = (int)gpus;
         if (pg_create(&q, &ctx)) { fprintf(stderr, "polar_sim: pg_create (GPU %d): %s\n", rank, pg_last_error(NULL)); return 3; }
         if (have_id && pg_comm_init(ctx, id)) die("pg_comm_init", ctx);
+        if (pd->fmt == F_BPR && pg_bpr_config(ctx, BPR_SAMPLES, 6)) die("pg_bpr_config", ctx);
     }
 
     ref_state st;
@@ -358,10 +389,19 @@ int main(int argc, char **argv)
         pg_counters c;
         struct timespec t0, t1;
         clock_gettime(CLOCK_MONOTONIC, &t0);
+        const int bpr = (pd->fmt == F_BPR);
+        memset(g_bprE, 0, sizeof(g_bprE));
         if (use_ref) {
-            ref_point(ctx, &p, bSNR_dB, (uint64_t)ble, (uint64_t)maxf, &st, &c);
+            ref_point(ctx, &p, bSNR_dB, (uint64_t)ble, (uint64_t)maxf, &st, &c, bpr);
         } else {
-            if (pg_simulate(ctx, bSNR_dB, next_frame, (uint64_t)ble, (uint64_t)maxf, 1, &c)) die("pg_simulate", ctx);
+            /* BPR counters are summed on the device over whole rounds, so the BPr program counts whole rounds too
+               (error block >= BLE) to keep E, run and the error counts on the same set of frames */
+            if (bpr && pg_bpr_reset(ctx)) die("pg_bpr_reset", ctx);
+            if (pg_simulate(ctx, bSNR_dB, next_frame, (uint64_t)ble, (uint64_t)maxf, bpr ? 0 : 1, &c)) die("pg_simulate", ctx);
+            if (bpr) {
+                if (gpus > 1) { fprintf(stderr, "polar_sim: BPr_128 supports one GPU\n"); return 2; }
+                if (pg_bpr_read(ctx, g_bprE)) die("pg_bpr_read", ctx);
+            }
         }
         clock_gettime(CLOCK_MONOTONIC, &t1);
         next_frame += c.frames;

@@ -52,3 +52,11 @@ def test_stdin_matrix_is_accepted_and_philox_mode_runs():
     assert "Mframes/s" in p.stderr
     out = run("SC_1024", "--ebn0", "2.0", "--ble", "10", "--real", "f64")
     assert out.startswith("bSNR = 2.00\terror block = 10\trun = ")
+
+
+def test_bpr128_reproduces_reference_stdout():
+    """BPr_128 with time() forced to 945: SEED line and the first two Eb/N0 points, byte for byte (run, six E rows, BLER/BER)"""
+    out = run("BPr_128", "--rng", "ref", "--seed", "945", "--ebn0", "1.0:0.5:1.5")
+    assert out == KAT["K_BPr_128"]["stdout"]
+    out = run("BPr_128", "--ebn0", "2.0", "--ble", "50", "--seed", "3")
+    assert "After 80 iterations:" in out and "K * BER" in out

@@ -88,6 +88,11 @@ kat["K2_SCL_128"] = {"seed": 1024, "target": 50, "ebn0": [1.0, 1.5, 2.0, 2.5],
 out = run_ref("CASCL_128", "Fn_128.txt", seed=8392)
 kat["K4_CASCL_128"] = {"seed": 8392, "target": 200, "ebn0": [1.0, 1.5, 2.0, 2.5, 3.0],
                        "run": [int(l.split("run = ")[1].split()[0]) for l in out.splitlines() if "run = " in l], "stdout": out}
+# BPr_128 (clock seed forced to 945): the full sweep takes minutes on one core, so the run is cut after the first points;
+# stdbuf makes the reference's buffered stdout visible before the kill
+r = subprocess.run(["timeout", "60", "stdbuf", "-o0", os.path.join(REF_DIR, "BPr_128")], stdin=open(os.path.join(REF_DIR, "Fn_128.txt")),
+                   capture_output=True, env=dict(os.environ, POLAR_REF_TIME="945"))
+kat["K_BPr_128"] = {"seed": 945, "ebn0": [1.0, 1.5], "stdout": "\n".join(r.stdout.decode().splitlines()[:29]) + "\n"}
 # the author's captures, for cross-checking the three above against the shipped result files
 cap = {}
 with zipfile.ZipFile("/root/reference/myResult_128.zip") as z:
