@@ -29,7 +29,7 @@ N, K_INFO = 1024, 512
 OPS_CASCL = 30016 * 27 + 35906 * 2 + 11185 * 11 + 533 * 160 + 36000 + 28000   # ~1.15 M lane-ops / frame
 OPS_BP_SWEEP = 573440                                                          # per sweep, N=1024
 EBN0_CASCL, EBN0_BP = 2.0, 2.5
-B_CASCL, B_BP = 1 << 16, 1 << 15                                               # frames per step (256 MB / 128 MB of fp32 LLRs)
+B_CASCL, B_BP = 1 << 16, 1 << 15                                               # target frames per step (~256 MB / 128 MB of fp32 LLRs), rounded to whole waves
 
 
 def peaks():
@@ -211,6 +211,8 @@ def run_gpu_arm(a):
             ids = [comm_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(ids, src=0)
             eng.comm_init(ids[0])
+        wave = eng.wave_frames()                      # frames a full grid decodes concurrently
+        B = max(1, round(B / wave)) * wave             # whole waves: every SM stays busy until the launch ends
         st = torch.cuda.ExternalStream(eng.stream_ptr())
         llr = torch.empty(B * N, dtype=torch.float32, device="cuda")
         truth = torch.empty(B * (N // 32), dtype=torch.int32, device="cuda")
@@ -238,7 +240,7 @@ def run_gpu_arm(a):
                             "hbm_gbs": (fps / world) * (N * 4 + 2 * (N // 8) + 4) / 1e9, "hbm_frac": (fps / world) * (N * 4 + 2 * (N // 8) + 4) / 1e9 / pk["hbm_gbs"]}}
         assert cnt.frames == world * B * steps_total, (cnt.frames, world, B, steps_total)
         # ---- e2e: host LLRs (pinned) -> C ABI -> host decisions, every step
-        Be = B // 4
+        Be = max(1, round(B / 4 / wave)) * wave
         h_llr = torch.empty(Be * N, dtype=torch.float32).pin_memory()
         h_llr.copy_(llr[: Be * N])
         h_out = torch.empty(Be * (N // 32), dtype=torch.int32).pin_memory()
@@ -272,7 +274,7 @@ def run_gpu_arm(a):
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "CASCL_1024_L8 (N=1024 K=512 r=24 L=8) at Eb/N0 %.1f dB, PN-63 payload, Philox AWGN" % EBN0_CASCL,
-                           "frames_per_step": r["frames_per_step"], "l2": "inputs larger than L2 (256 MB of LLRs per GPU per step)",
+                           "frames_per_step": r["frames_per_step"], "l2": "inputs larger than L2 (%d MB of LLRs per GPU per step)" % (r["frames_per_step"] // world * N * 4 >> 20),
                            "arith": "fp32 throughput mode; fp64 parity mode is bit-exact with the reference (tests/test_gpu_parity.py)",
                            "partition": "rank r decodes its own Philox frame range; one NCCL all-reduce of the final counters"},
                 "frames_per_s": r["frames_per_s"], "fer": r["fer"], "tie_frames": r["tie_frames"], "frames_counted": r["frames_counted"],

@@ -167,6 +167,9 @@ int pg_merge_round(const pg_counters *round, int nranks, uint64_t target, int ex
 int pg_truncate_info(const uint32_t *frame_info, size_t nframes, uint64_t need, pg_counters *part);
 
 /* ---- introspection for benches ------------------------------------------------------------------------ */
+/* frames one full grid of the decode kernel holds at a time (resident CTAs x frames per CTA): batch sizes that are a
+ * multiple of this keep every SM busy until the end of a launch */
+uint64_t pg_wave_frames(const pg_ctx *ctx);
 int pg_sync(pg_ctx *ctx);                              /* cudaStreamSynchronize on the ctx stream */
 void *pg_stream(pg_ctx *ctx);                          /* the cudaStream_t the kernels are launched on */
 uint64_t pg_kernel_launches(const pg_ctx *ctx);        /* kernels launched by this context so far */

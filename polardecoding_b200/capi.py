@@ -68,6 +68,8 @@ def load_library():
     lib.pg_comm_unique_id.argtypes = [vp]
     lib.pg_comm_init.argtypes = [vp, vp]
     lib.pg_allreduce_counters.argtypes = [vp, C.POINTER(PgCounters)]
+    lib.pg_wave_frames.argtypes = [vp]
+    lib.pg_wave_frames.restype = C.c_uint64
     lib.pg_sync.argtypes = [vp]
     lib.pg_stream.argtypes = [vp]
     lib.pg_stream.restype = vp
@@ -217,6 +219,9 @@ class Engine:
     def comm_init(self, id128: bytes):
         buf = C.create_string_buffer(id128, 128)
         self._check(self.lib.pg_comm_init(self.ctx, buf), "pg_comm_init")
+
+    def wave_frames(self):
+        return int(self.lib.pg_wave_frames(self.ctx))
 
     def sync(self):
         self._check(self.lib.pg_sync(self.ctx), "pg_sync")

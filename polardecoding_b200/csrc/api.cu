@@ -260,7 +260,9 @@ extern "C" int pg_create(const pg_params *p, pg_ctx **out)
         cudaError_t pe = list_plan(ctx->n, L, ctx->f64, &lp);
         if (pe != cudaSuccess) { ctx->err = std::string("no list kernel for this (N, L): ") + cudaGetErrorString(pe); return bail(PG_ERR_UNSUPPORTED); }
         if (lp.ctas_per_sm < 1) { ctx->err = "list kernel does not fit on an SM"; return bail(PG_ERR_UNSUPPORTED); }
-        ctx->grid = ctx->sm_count * lp.ctas_per_sm;
+        int per_sm = lp.ctas_per_sm;
+        if (const char *cap = getenv("POLARGPU_LIST_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(cap)));  // tuning aid
+        ctx->grid = ctx->sm_count * per_sm;
         if (lp.scratch_per_cta) CUC(cudaMalloc(&ctx->d_scratch, lp.scratch_per_cta * (size_t)ctx->grid));
     }
     {
@@ -691,6 +693,13 @@ extern "C" int pg_sync(pg_ctx *ctx)
     CU(cudaSetDevice(ctx->p.device));
     CU(cudaStreamSynchronize(ctx->st));
     return PG_OK;
+}
+
+extern "C" uint64_t pg_wave_frames(const pg_ctx *ctx)
+{
+    if (!ctx) return 0;
+    const uint64_t per_cta = (ctx->p.decoder == PG_DEC_BP) ? 1 : (uint64_t)(32 / ctx->p.list_size);
+    return (uint64_t)ctx->grid * per_cta;
 }
 
 extern "C" void *pg_stream(pg_ctx *ctx) { return ctx ? (void *)ctx->st : nullptr; }

@@ -183,8 +183,15 @@ __global__ void __launch_bounds__(32) list_decode_kernel(const ListArgs a)
                 int stride = 1;
                 if (s + 1 != LOGN) { src = stage_at(s + 1) + fbase + pfield(s + 1); stride = 32; }
                 const V4 *src2 = src + cnt4 * stride;
+                // scratch / channel operands come from L2 or HBM: fetch the next pair while the current four CHKs run
+                V4 x = ldv(src), y = ldv(src2);
 #pragma unroll 1
-                for (int i4 = 0; i4 < cnt4; i4++, dst += 32, src += stride, src2 += stride) stv(dst, f4<real>(ldv(src), ldv(src2)));
+                for (int i4 = 0; i4 < cnt4; i4++, dst += 32) {
+                    V4 nx = x, ny = y;
+                    if (i4 + 1 < cnt4) { src += stride; src2 += stride; nx = ldv(src); ny = ldv(src2); }
+                    stv(dst, f4<real>(x, y));
+                    x = nx; y = ny;
+                }
             }
             set_pfield(s);
             __syncwarp();
@@ -213,12 +220,20 @@ __global__ void __launch_bounds__(32) list_decode_kernel(const ListArgs a)
 #pragma unroll 1
                 for (int i4 = 0; i4 < cnt4; i4++, dst += 32, src += stride, src2 += stride, bw >>= 4) stv(dst, g4<real>(ldv(src), ldv(src2), bw & 0xFu));
             } else {
+                // a g-layer is one add per node: memory bound.  Eight independent 128-bit loads in flight per lane.
                 const uint32_t *bsrc = bits_at(t) + fbase + bfield(t);
 #pragma unroll 1
                 for (int w = 0; w < (cnt4 >> 3); w++, bsrc += 32) {
                     uint32_t bw = *bsrc;
-#pragma unroll 2
-                    for (int q = 0; q < 8; q++, dst += 32, src += stride, src2 += stride, bw >>= 4) stv(dst, g4<real>(ldv(src), ldv(src2), bw & 0xFu));
+#pragma unroll 1
+                    for (int h = 0; h < 2; h++) {
+                        V4 up[4], lo[4];
+#pragma unroll
+                        for (int q = 0; q < 4; q++) { up[q] = ldv(src + q * stride); lo[q] = ldv(src2 + q * stride); }
+#pragma unroll
+                        for (int q = 0; q < 4; q++) stv(dst + q * 32, g4<real>(up[q], lo[q], (bw >> (4 * q)) & 0xFu));
+                        dst += 4 * 32; src += 4 * stride; src2 += 4 * stride; bw >>= 16;
+                    }
                 }
             }
             set_pfield(t);
