@@ -93,6 +93,10 @@ kat["K4_CASCL_128"] = {"seed": 8392, "target": 200, "ebn0": [1.0, 1.5, 2.0, 2.5,
 r = subprocess.run(["timeout", "60", "stdbuf", "-o0", os.path.join(REF_DIR, "BPr_128")], stdin=open(os.path.join(REF_DIR, "Fn_128.txt")),
                    capture_output=True, env=dict(os.environ, POLAR_REF_TIME="945"))
 kat["K_BPr_128"] = {"seed": 945, "ebn0": [1.0, 1.5], "stdout": "\n".join(r.stdout.decode().splitlines()[:29]) + "\n"}
+# deterministic DE-GA analysis programs (K8): stdout of the compiled reference, verbatim
+for prog in ("BPDEGA_128", "BPRGA_128", "BPRGA_1024", "BPRGA_128_allbit"):
+    out = subprocess.run([os.path.join(REF_DIR, prog)], stdin=subprocess.DEVNULL, capture_output=True, timeout=120).stdout
+    open(os.path.join(OUT, "ga_%s.txt" % prog), "wb").write(out)
 # the author's captures, for cross-checking the three above against the shipped result files
 cap = {}
 with zipfile.ZipFile("/root/reference/myResult_128.zip") as z:
