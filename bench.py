@@ -240,7 +240,7 @@ def run_gpu_arm(a):
                             "hbm_gbs": (fps / world) * (N * 4 + 2 * (N // 8) + 4) / 1e9, "hbm_frac": (fps / world) * (N * 4 + 2 * (N // 8) + 4) / 1e9 / pk["hbm_gbs"]}}
         assert cnt.frames == world * B * steps_total, (cnt.frames, world, B, steps_total)
         # ---- e2e: host LLRs (pinned) -> C ABI -> host decisions, every step
-        Be = max(1, round(B / 4 / wave)) * wave
+        Be = B                                         # whole waves; the C ABI pipelines H2D of wave i+1 with the decode of wave i
         h_llr = torch.empty(Be * N, dtype=torch.float32).pin_memory()
         h_llr.copy_(llr[: Be * N])
         h_out = torch.empty(Be * (N // 32), dtype=torch.int32).pin_memory()

@@ -84,6 +84,13 @@ struct pg_ctx {
     unsigned long long *h_counters = nullptr;  // pinned, CNT_N
     void *d_scratch = nullptr;
     int grid = 0;
+    // second buffer set + copy stream for the pipelined host path (pg_decode_llr*: H2D of chunk i+1 overlaps decode of chunk i)
+    cudaStream_t st_copy = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    size_t pipe_cap = 0;
+    void *p_llr[2] = {nullptr, nullptr}, *p_in[2] = {nullptr, nullptr};
+    uint32_t *p_uhat[2] = {nullptr, nullptr}, *p_info[2] = {nullptr, nullptr};
+    uint8_t *p_bytes[2] = {nullptr, nullptr};
     size_t chunk_max = 0;
 
     ncclComm_t comm = nullptr;
@@ -154,6 +161,30 @@ static void free_buffers(pg_ctx *ctx)
     if (ctx->h_info) cudaFreeHost(ctx->h_info);
     ctx->d_llr = ctx->d_in = nullptr; ctx->d_truth = ctx->d_uhat = ctx->d_info = nullptr; ctx->d_bytes = nullptr; ctx->h_info = nullptr;
     ctx->cap = 0;
+}
+
+static int ensure_pipe(pg_ctx *ctx, size_t frames, bool want_bytes)
+{
+    if (!ctx->st_copy) {
+        CU(cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking));
+        for (int s = 0; s < 2; s++) {
+            CU(cudaEventCreateWithFlags(&ctx->ev_h2d[s], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&ctx->ev_free[s], cudaEventDisableTiming));
+        }
+    }
+    if (frames <= ctx->pipe_cap && (!want_bytes || ctx->p_bytes[0])) return PG_OK;
+    const size_t N = ctx->p.N, W = ctx->W;
+    for (int s = 0; s < 2; s++) {
+        cudaFree(ctx->p_llr[s]); cudaFree(ctx->p_in[s]); cudaFree(ctx->p_uhat[s]); cudaFree(ctx->p_info[s]); cudaFree(ctx->p_bytes[s]);
+        ctx->p_llr[s] = ctx->p_in[s] = nullptr; ctx->p_uhat[s] = ctx->p_info[s] = nullptr; ctx->p_bytes[s] = nullptr;
+        CU(cudaMalloc(&ctx->p_llr[s], frames * N * (ctx->f64 ? 8 : 4)));
+        CU(cudaMalloc(&ctx->p_in[s], frames * N * (ctx->f64 ? 4 : 8)));
+        CU(cudaMalloc(&ctx->p_uhat[s], frames * W * 4));
+        CU(cudaMalloc(&ctx->p_info[s], frames * 4));
+        if (want_bytes) CU(cudaMalloc(&ctx->p_bytes[s], frames * N));
+    }
+    ctx->pipe_cap = frames;
+    return PG_OK;
 }
 
 static int ensure_capacity(pg_ctx *ctx, size_t frames)
@@ -282,6 +313,12 @@ extern "C" void pg_destroy(pg_ctx *ctx)
     if (ctx->st) cudaStreamSynchronize(ctx->st);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     free_buffers(ctx);
+    for (int s = 0; s < 2; s++) {
+        cudaFree(ctx->p_llr[s]); cudaFree(ctx->p_in[s]); cudaFree(ctx->p_uhat[s]); cudaFree(ctx->p_info[s]); cudaFree(ctx->p_bytes[s]);
+        if (ctx->ev_h2d[s]) cudaEventDestroy(ctx->ev_h2d[s]);
+        if (ctx->ev_free[s]) cudaEventDestroy(ctx->ev_free[s]);
+    }
+    if (ctx->st_copy) cudaStreamDestroy(ctx->st_copy);
     cudaFree(ctx->d_I); cudaFree(ctx->d_crc_masks); cudaFree(ctx->d_crc_sys); cudaFree(ctx->d_counters); cudaFree(ctx->d_queue);
     cudaFree(ctx->d_bpr); cudaFree(ctx->d_scratch); cudaFree(ctx->d_xchg);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
@@ -428,6 +465,14 @@ extern "C" int pg_channel_device(pg_ctx *ctx, double ebn0_db, uint64_t first_fra
     return run_channel_to(ctx, ebn0_db, first_frame, B, d_llr, d_u_packed);
 }
 
+static uint64_t wave_frames(const pg_ctx *ctx)
+{
+    const uint64_t per_cta = (ctx->p.decoder == PG_DEC_BP) ? 1 : (uint64_t)(32 / ctx->p.list_size);
+    return (uint64_t)ctx->grid * per_cta;
+}
+
+// Host-pointer decode.  Batches larger than one wave of the decode kernel are cut into wave-sized chunks and pipelined over
+// two buffer sets: the H2D copy of chunk i+1 (copy stream) overlaps the decode + D2H of chunk i (compute stream).
 static int decode_host(pg_ctx *ctx, const void *llr, int llr_is_f64, size_t B, uint8_t *u_hat, uint32_t *u_hat_packed, uint32_t *flags)
 {
     if (!ctx || !llr) return PG_ERR_ARG;
@@ -435,27 +480,65 @@ static int decode_host(pg_ctx *ctx, const void *llr, int llr_is_f64, size_t B, u
     const size_t N = ctx->p.N, W = ctx->W;
     const size_t esz = llr_is_f64 ? 8 : 4;
     const bool conv = (llr_is_f64 != 0) != ctx->f64;
-    for (size_t off = 0; off < B; off += ctx->chunk_max) {
-        const size_t b = std::min(ctx->chunk_max, B - off);
-        int rc = ensure_capacity(ctx, b);
+    const size_t pc = std::min<size_t>(ctx->chunk_max, std::max<size_t>((size_t)wave_frames(ctx), 1024));
+    if (B > pc && !getenv("POLARGPU_NO_PIPELINE")) {
+        int rc = ensure_pipe(ctx, pc, u_hat != nullptr);
         if (rc) return rc;
-        void *dst = conv ? ctx->d_in : ctx->d_llr;
-        CU(cudaMemcpyAsync(dst, (const char *)llr + off * N * esz, b * N * esz, cudaMemcpyHostToDevice, ctx->st));
-        if (conv) { CU(launch_convert_llr(ctx->d_in, llr_is_f64 != 0, ctx->d_llr, ctx->f64, b * N, ctx->st)); ctx->launches++; }
-        rc = run_decode(ctx, ctx->d_llr, b, nullptr, ctx->d_uhat, ctx->d_info, false);
-        if (rc) return rc;
-        if (u_hat) {
-            CU(launch_unpack_bits(ctx->d_uhat, ctx->d_bytes, b, (int)N, ctx->st));
-            ctx->launches++;
-            CU(cudaMemcpyAsync(u_hat + off * N, ctx->d_bytes, b * N, cudaMemcpyDeviceToHost, ctx->st));
+        size_t i = 0;
+        for (size_t off = 0; off < B; off += pc, i++) {
+            const size_t b = std::min(pc, B - off);
+            const int s = (int)(i & 1);
+            if (i >= 2) CU(cudaStreamWaitEvent(ctx->st_copy, ctx->ev_free[s], 0));
+            void *dst = conv ? ctx->p_in[s] : ctx->p_llr[s];
+            CU(cudaMemcpyAsync(dst, (const char *)llr + off * N * esz, b * N * esz, cudaMemcpyHostToDevice, ctx->st_copy));
+            CU(cudaEventRecord(ctx->ev_h2d[s], ctx->st_copy));
+            CU(cudaStreamWaitEvent(ctx->st, ctx->ev_h2d[s], 0));
+            if (conv) { CU(launch_convert_llr(ctx->p_in[s], llr_is_f64 != 0, ctx->p_llr[s], ctx->f64, b * N, ctx->st)); ctx->launches++; }
+            rc = run_decode(ctx, ctx->p_llr[s], b, nullptr, ctx->p_uhat[s], ctx->p_info[s], false);
+            if (rc) return rc;
+            if (u_hat) {
+                CU(launch_unpack_bits(ctx->p_uhat[s], ctx->p_bytes[s], b, (int)N, ctx->st));
+                ctx->launches++;
+                CU(cudaMemcpyAsync(u_hat + off * N, ctx->p_bytes[s], b * N, cudaMemcpyDeviceToHost, ctx->st));
+            }
+            if (u_hat_packed) CU(cudaMemcpyAsync(u_hat_packed + off * W, ctx->p_uhat[s], b * W * 4, cudaMemcpyDeviceToHost, ctx->st));
+            if (flags) CU(cudaMemcpyAsync(flags + off, ctx->p_info[s], b * 4, cudaMemcpyDeviceToHost, ctx->st));
+            CU(cudaEventRecord(ctx->ev_free[s], ctx->st));
         }
-        if (u_hat_packed) CU(cudaMemcpyAsync(u_hat_packed + off * W, ctx->d_uhat, b * W * 4, cudaMemcpyDeviceToHost, ctx->st));
-        if (flags) CU(cudaMemcpyAsync(flags + off, ctx->d_info, b * 4, cudaMemcpyDeviceToHost, ctx->st));
         CU(cudaStreamSynchronize(ctx->st));
+    } else {
+        for (size_t off = 0; off < B; off += ctx->chunk_max) {
+            const size_t b = std::min(ctx->chunk_max, B - off);
+            int rc = ensure_capacity(ctx, b);
+            if (rc) return rc;
+            void *dst = conv ? ctx->d_in : ctx->d_llr;
+            CU(cudaMemcpyAsync(dst, (const char *)llr + off * N * esz, b * N * esz, cudaMemcpyHostToDevice, ctx->st));
+            if (conv) { CU(launch_convert_llr(ctx->d_in, llr_is_f64 != 0, ctx->d_llr, ctx->f64, b * N, ctx->st)); ctx->launches++; }
+            rc = run_decode(ctx, ctx->d_llr, b, nullptr, ctx->d_uhat, ctx->d_info, false);
+            if (rc) return rc;
+            if (u_hat) {
+                CU(launch_unpack_bits(ctx->d_uhat, ctx->d_bytes, b, (int)N, ctx->st));
+                ctx->launches++;
+                CU(cudaMemcpyAsync(u_hat + off * N, ctx->d_bytes, b * N, cudaMemcpyDeviceToHost, ctx->st));
+            }
+            if (u_hat_packed) CU(cudaMemcpyAsync(u_hat_packed + off * W, ctx->d_uhat, b * W * 4, cudaMemcpyDeviceToHost, ctx->st));
+            if (flags) CU(cudaMemcpyAsync(flags + off, ctx->d_info, b * 4, cudaMemcpyDeviceToHost, ctx->st));
+            CU(cudaStreamSynchronize(ctx->st));
+        }
     }
     if (flags)
         for (size_t i = 0; i < B; i++) flags[i] = ((flags[i] >> 16) & 3u) | ((flags[i] >> 24) << 8);
     return PG_OK;
+}
+
+extern "C" int pg_decode_llr(pg_ctx *ctx, const void *llr, int llr_is_f64, size_t B, uint8_t *u_hat, uint32_t *flags)
+{
+    return decode_host(ctx, llr, llr_is_f64, B, u_hat, nullptr, flags);
+}
+
+extern "C" int pg_decode_llr_packed(pg_ctx *ctx, const void *llr, int llr_is_f64, size_t B, uint32_t *u_hat_packed, uint32_t *flags)
+{
+    return decode_host(ctx, llr, llr_is_f64, B, nullptr, u_hat_packed, flags);
 }
 
 extern "C" int pg_decode_llr_counted(pg_ctx *ctx, const void *llr, int llr_is_f64, size_t B, const uint8_t *u_true, uint8_t *u_hat,
@@ -495,16 +578,6 @@ extern "C" int pg_decode_llr_counted(pg_ctx *ctx, const void *llr, int llr_is_f6
             for (size_t i = 0; i < b; i++) frame_err[off + i] = (uint16_t)(ctx->h_info[i] & 0xFFFFu);
     }
     return PG_OK;
-}
-
-extern "C" int pg_decode_llr(pg_ctx *ctx, const void *llr, int llr_is_f64, size_t B, uint8_t *u_hat, uint32_t *flags)
-{
-    return decode_host(ctx, llr, llr_is_f64, B, u_hat, nullptr, flags);
-}
-
-extern "C" int pg_decode_llr_packed(pg_ctx *ctx, const void *llr, int llr_is_f64, size_t B, uint32_t *u_hat_packed, uint32_t *flags)
-{
-    return decode_host(ctx, llr, llr_is_f64, B, nullptr, u_hat_packed, flags);
 }
 
 extern "C" int pg_channel(pg_ctx *ctx, double ebn0_db, uint64_t first_frame, size_t B, void *llr_out, uint8_t *u_out)
@@ -695,12 +768,7 @@ extern "C" int pg_sync(pg_ctx *ctx)
     return PG_OK;
 }
 
-extern "C" uint64_t pg_wave_frames(const pg_ctx *ctx)
-{
-    if (!ctx) return 0;
-    const uint64_t per_cta = (ctx->p.decoder == PG_DEC_BP) ? 1 : (uint64_t)(32 / ctx->p.list_size);
-    return (uint64_t)ctx->grid * per_cta;
-}
+extern "C" uint64_t pg_wave_frames(const pg_ctx *ctx) { return ctx ? wave_frames(ctx) : 0; }
 
 extern "C" void *pg_stream(pg_ctx *ctx) { return ctx ? (void *)ctx->st : nullptr; }
 extern "C" uint64_t pg_kernel_launches(const pg_ctx *ctx) { return ctx ? ctx->launches : 0; }

@@ -153,3 +153,23 @@ def test_edge_inputs():
     assert (got == want).all(), describe(got, want, flags)
     assert ((flags & 1) == (aux & 1)).all()
     eng.close()
+
+
+def test_pipelined_host_path_equals_single_chunk():
+    """pg_decode_llr cuts batches larger than one wave into chunks and overlaps copies with decoding: same answers"""
+    import os
+    from polardecoding_b200 import Engine
+    eng = Engine("SC_128", real="f32")
+    B = 3 * eng.wave_frames() + 77          # several chunks and a ragged tail
+    rng = np.random.default_rng(0)
+    llr = (rng.standard_normal((B, 128)) * 3 + 2).astype(np.float32)
+    got, flags = eng.decode_llr(llr, packed=True)
+    os.environ["POLARGPU_NO_PIPELINE"] = "1"
+    try:
+        want, _ = eng.decode_llr(llr, packed=True)
+    finally:
+        del os.environ["POLARGPU_NO_PIPELINE"]
+    assert (got == want).all()
+    full, _ = eng.decode_llr(llr[:1000])
+    assert (np.packbits(full, axis=1, bitorder="little").view(np.uint32) == want[:1000]).all()
+    eng.close()
