@@ -32,6 +32,23 @@ struct BpCfg {
     static constexpr size_t SMEM = MSG * sizeof(real) + (size_t)(W + 4) * 4;
 };
 
+// two neighbouring messages as one 64/128-bit shared-memory access
+template <typename real> struct pair_t;
+template <> struct pair_t<float> { using type = float2; };
+template <> struct pair_t<double> { using type = double2; };
+template <typename real>
+__device__ __forceinline__ void ld2(const real *p, real &a, real &b)
+{
+    const typename pair_t<real>::type v = *reinterpret_cast<const typename pair_t<real>::type *>(p);
+    a = v.x; b = v.y;
+}
+template <typename real>
+__device__ __forceinline__ void st2(real *p, real a, real b)
+{
+    typename pair_t<real>::type v; v.x = a; v.y = b;
+    *reinterpret_cast<typename pair_t<real>::type *>(p) = v;
+}
+
 template <int THREADS>
 __device__ __forceinline__ void cta_sync()
 {
@@ -72,7 +89,7 @@ __global__ void __launch_bounds__(THREADS) bp_decode_kernel(const BpArgs a)
         real ch_up[BPT], ch_lo[BPT];
 #pragma unroll
         for (int i = 0; i < BPT; i++) {
-            const int q = tid + i * THREADS;
+            const int q = (BPT == 2) ? (2 * tid + i) : (tid + i * THREADS);
             ch_up[i] = __ldg(llr + q);
             ch_lo[i] = __ldg(llr + q + N / 2);
         }
@@ -96,7 +113,8 @@ __global__ void __launch_bounds__(THREADS) bp_decode_kernel(const BpArgs a)
                         su = chk<real>(lu, ll + rl) + ru;
                         sl = (ll + chk<real>(ru, lu)) + rl;
                     } else if (i == n) {  // r(n,.) is not state: form it from r(n-1,.), l(n,.) = channel
-                        ju = qq; jl = qq + N / 2;
+                        ju = (BPT == 2) ? (2 * tid + e) : qq;  // the positions whose channel LLRs this thread holds
+                        jl = ju + N / 2;
                         const real *rin = Rm + (size_t)(n - 2) * N;
                         const real ru = (n == 1) ? r0(ju) : rin[ju], rl = (n == 1) ? r0(jl) : rin[jl];
                         su = ch_up[e] + chk<real>(ru, ch_lo[e] + rl);
@@ -131,6 +149,34 @@ __global__ void __launch_bounds__(THREADS) bp_decode_kernel(const BpArgs a)
         int sweeps = 0;
         for (int it = 0; it < a.iters; it++) {
             // ---- R pass, stages 0..n-2 (stage n-1 would only produce r(n), which nothing reads)
+            if (BPT == 2) {
+                // a thread owns two NEIGHBOURING butterflies (2*tid, 2*tid+1): for s >= 1 their upper nodes j, j+1 and their
+                // lower nodes j+d, j+d+1 are adjacent, so every message pair moves as one 64-bit access
+                {   // s = 0: butterflies (4t,4t+1) and (4t+2,4t+3)
+                    const int j = 4 * tid;
+                    real l0, l1, l2, l3;
+                    ld2<real>(Lm + j, l0, l1);
+                    ld2<real>(Lm + j + 2, l2, l3);
+                    const real ra = r0(j), rb = r0(j + 1), rc = r0(j + 2), rd = r0(j + 3);
+                    st2<real>(Rm + j, chk<real>(ra, l1 + rb), rb + chk<real>(ra, l0));
+                    st2<real>(Rm + j + 2, chk<real>(rc, l3 + rd), rd + chk<real>(rc, l2));
+                    cta_sync<THREADS>();
+                }
+                for (int s = 1; s < n - 1; s++) {
+                    const int d = 1 << s, q = 2 * tid;
+                    const int j = ((q >> s) << (s + 1)) | (q & (d - 1));
+                    const real *rin = Rm + (size_t)(s - 1) * N, *lin = Lm + (size_t)s * N;
+                    real *rout = Rm + (size_t)s * N;
+                    real ru0, ru1, rl0, rl1, lu0, lu1, ll0, ll1;
+                    ld2<real>(rin + j, ru0, ru1);
+                    ld2<real>(rin + j + d, rl0, rl1);
+                    ld2<real>(lin + j, lu0, lu1);
+                    ld2<real>(lin + j + d, ll0, ll1);
+                    st2<real>(rout + j, chk<real>(ru0, ll0 + rl0), chk<real>(ru1, ll1 + rl1));
+                    st2<real>(rout + j + d, rl0 + chk<real>(ru0, lu0), rl1 + chk<real>(ru1, lu1));
+                    cta_sync<THREADS>();
+                }
+            } else
             for (int s = 0; s < n - 1; s++) {
                 const int d = 1 << s;
                 const real *rin = Rm + (size_t)(s - 1) * N;
@@ -150,6 +196,30 @@ __global__ void __launch_bounds__(THREADS) bp_decode_kernel(const BpArgs a)
             }
             // ---- L pass, stages n-1..1
             int changed = 0;
+            if (BPT == 2) {
+                for (int s = n - 1; s >= 1; s--) {
+                    const int d = 1 << s, q = 2 * tid;
+                    const int j = ((q >> s) << (s + 1)) | (q & (d - 1));
+                    const real *rin = Rm + (size_t)(s - 1) * N, *lin = Lm + (size_t)s * N;
+                    real *lout = Lm + (size_t)(s - 1) * N;
+                    real ru0, ru1, rl0, rl1, lu0, lu1, ll0, ll1;
+                    if (s == n - 1) { lu0 = ch_up[0]; lu1 = ch_up[1]; ll0 = ch_lo[0]; ll1 = ch_lo[1]; }
+                    else { ld2<real>(lin + j, lu0, lu1); ld2<real>(lin + j + d, ll0, ll1); }
+                    ld2<real>(rin + j, ru0, ru1);
+                    ld2<real>(rin + j + d, rl0, rl1);
+                    const real ou0 = chk<real>(lu0, ll0 + rl0), ou1 = chk<real>(lu1, ll1 + rl1);
+                    const real ol0 = ll0 + chk<real>(ru0, lu0), ol1 = ll1 + chk<real>(ru1, lu1);
+                    if (a.early_stop) {
+                        real pu0, pu1, pl0, pl1;
+                        ld2<real>(lout + j, pu0, pu1);
+                        ld2<real>(lout + j + d, pl0, pl1);
+                        changed |= (int)(!RT::same_bits(ou0, pu0)) | (int)(!RT::same_bits(ou1, pu1)) | (int)(!RT::same_bits(ol0, pl0)) | (int)(!RT::same_bits(ol1, pl1));
+                    }
+                    st2<real>(lout + j, ou0, ou1);
+                    st2<real>(lout + j + d, ol0, ol1);
+                    cta_sync<THREADS>();
+                }
+            } else
             for (int s = n - 1; s >= 1; s--) {
                 const int d = 1 << s;
                 const real *rin = Rm + (size_t)(s - 1) * N;  // r(s,.)
