@@ -204,7 +204,12 @@ def run_gpu_arm(a):
     launches = 0
     res = {}
 
-    def bench_one(prog, ebn0, B, ops_per_frame, **over):
+    try:
+        traffic_db = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+    except Exception:
+        traffic_db = {}
+
+    def bench_one(prog, ebn0, B, ops_per_frame, tkey=None, **over):
         nonlocal launches
         eng = Engine(prog, real="f32", device=local, rank=rank, nranks=world, seed=1024, data_mode=0, **over)
         if world > 1:  # the library's own NCCL communicator: the id travels over torch.distributed
@@ -238,6 +243,11 @@ def run_gpu_arm(a):
                "roofline": {"bound": "alu", "achieved": (fps / world) * ops / 1e12, "peak": peak_ops / 1e12, "unit": "Tlaneop/s",
                             "frac": (fps / world) * ops / peak_ops, "traffic": None, "ops_per_frame": ops, "peak_source": pk_src + " sm_max_mhz x 148 SMs x 128 lanes",
                             "hbm_gbs": (fps / world) * (N * 4 + 2 * (N // 8) + 4) / 1e9, "hbm_frac": (fps / world) * (N * 4 + 2 * (N // 8) + 4) / 1e9 / pk["hbm_gbs"]}}
+        tr = traffic_db.get(tkey) if tkey else None
+        if tr:  # DRAM bytes of this kernel from the committed ncu --set full capture, scaled to this launch's frame count
+            out["roofline"]["traffic"] = tr["dram_bytes_per_launch"] * B / tr["frames_per_launch"]
+            out["roofline"]["traffic_source"] = "profiles/r1_traffic.json (ncu dram__bytes_read+write, %d-frame launch)" % tr["frames_per_launch"]
+            out["roofline"]["algorithmic_bytes"] = B * (N * 4 + 2 * (N // 8) + 4)
         assert cnt.frames == world * B * steps_total, (cnt.frames, world, B, steps_total)
         # ---- e2e: host LLRs (pinned) -> C ABI -> host decisions, every step
         Be = B                                         # whole waves; the C ABI pipelines H2D of wave i+1 with the decode of wave i
@@ -256,8 +266,8 @@ def run_gpu_arm(a):
         return out
 
     sampler.start()
-    res["cascl"] = bench_one("CASCL_1024_L8", EBN0_CASCL, B_CASCL, OPS_CASCL)
-    res["bp"] = bench_one("BP_1024", EBN0_BP, B_BP, OPS_BP_SWEEP * 100)
+    res["cascl"] = bench_one("CASCL_1024_L8", EBN0_CASCL, B_CASCL, OPS_CASCL, tkey="cascl")
+    res["bp"] = bench_one("BP_1024", EBN0_BP, B_BP, OPS_BP_SWEEP * 100, tkey="bp")
     res["bp_stop"] = bench_one("BP_1024", EBN0_BP, B_BP, 0, bp_early_stop=1)
     clocks = sampler.stop()
 
