@@ -209,9 +209,9 @@ def run_gpu_arm(a):
     except Exception:
         traffic_db = {}
 
-    def bench_one(prog, ebn0, B, ops_per_frame, tkey=None, **over):
+    def bench_one(prog, ebn0, B, ops_per_frame, tkey=None, real="f32", e2e=True, **over):
         nonlocal launches
-        eng = Engine(prog, real="f32", device=local, rank=rank, nranks=world, seed=1024, data_mode=0, **over)
+        eng = Engine(prog, real=real, device=local, rank=rank, nranks=world, seed=1024, data_mode=0, **over)
         if world > 1:  # the library's own NCCL communicator: the id travels over torch.distributed
             ids = [comm_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(ids, src=0)
@@ -219,7 +219,7 @@ def run_gpu_arm(a):
         wave = eng.wave_frames()                      # frames a full grid decodes concurrently
         B = max(1, round(B / wave)) * wave             # whole waves: every SM stays busy until the launch ends
         st = torch.cuda.ExternalStream(eng.stream_ptr())
-        llr = torch.empty(B * N, dtype=torch.float32, device="cuda")
+        llr = torch.empty(B * N, dtype=torch.float64 if real == "f64" else torch.float32, device="cuda")
         truth = torch.empty(B * (N // 32), dtype=torch.int32, device="cuda")
         info = torch.empty(B, dtype=torch.int32, device="cuda")
         first = (1 << 32) + rank * B                                  # disjoint Philox frame ranges per rank
@@ -249,6 +249,10 @@ def run_gpu_arm(a):
             out["roofline"]["traffic_source"] = "profiles/r1_traffic.json (ncu dram__bytes_read+write, %d-frame launch)" % tr["frames_per_launch"]
             out["roofline"]["algorithmic_bytes"] = B * (N * 4 + 2 * (N // 8) + 4)
         assert cnt.frames == world * B * steps_total, (cnt.frames, world, B, steps_total)
+        if not e2e:
+            eng.close()
+            del llr, truth, info
+            return out
         # ---- e2e: host LLRs (pinned) -> C ABI -> host decisions, every step
         Be = B                                         # whole waves; the C ABI pipelines H2D of wave i+1 with the decode of wave i
         h_llr = torch.empty(Be * N, dtype=torch.float32).pin_memory()
@@ -269,6 +273,9 @@ def run_gpu_arm(a):
     res["cascl"] = bench_one("CASCL_1024_L8", EBN0_CASCL, B_CASCL, OPS_CASCL, tkey="cascl")
     res["bp"] = bench_one("BP_1024", EBN0_BP, B_BP, OPS_BP_SWEEP * 100, tkey="bp")
     res["bp_stop"] = bench_one("BP_1024", EBN0_BP, B_BP, 0, bp_early_stop=1)
+    # the bit-exact (fp64) instantiation of both kernels, device-resident inputs only
+    res["cascl64"] = bench_one("CASCL_1024_L8", EBN0_CASCL, B_CASCL // 4, OPS_CASCL, real="f64", e2e=False)
+    res["bp64"] = bench_one("BP_1024", EBN0_BP, B_BP // 8, OPS_BP_SWEEP * 100, real="f64", e2e=False)
     clocks = sampler.stop()
 
     cpu = None
@@ -295,6 +302,9 @@ def run_gpu_arm(a):
                             "fixed_point_stop": {"value": res["bp_stop"]["gbps"], "frames_per_s": res["bp_stop"]["frames_per_s"],
                                                  "sweeps_per_frame": res["bp_stop"]["sweeps_per_frame"], "fer": res["bp_stop"]["fer"],
                                                  "roofline": res["bp_stop"]["roofline"], "note": "same decisions as 100 sweeps (bit-exact stop)"}}}
+        line["f64_parity_mode"] = {"note": "same kernels instantiated in double: decisions bit-exact with the reference (tests/test_gpu_parity.py)",
+                                   "cascl_1024_l8": {"value": res["cascl64"]["gbps"], "unit": "Gbit/s", "frames_per_s": res["cascl64"]["frames_per_s"], "fer": res["cascl64"]["fer"]},
+                                   "bp_1024": {"value": res["bp64"]["gbps"], "unit": "Gbit/s", "frames_per_s": res["bp64"]["frames_per_s"], "fer": res["bp64"]["fer"]}}
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
