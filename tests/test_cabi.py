@@ -75,3 +75,20 @@ def test_host_logic_partition_and_merge():
         got.append((s.value, c.value))
     assert got == [(1000, 256), (1256, 256), (1512, 88), (1768, 0)]
     assert lib.pg_partition(0, 0, 4, 0, 1, C.byref(s), C.byref(c)) != 0
+
+
+def test_fp32_table_increments_land_on_the_literals():
+    """polar_common.cuh forms the 8-level table in fp32 as a running sum of increments (FMA pipe); each partial sum must
+    equal the fp32 literal the reference's table holds (0.05f ... 0.65f), so the form is bit-identical to compare/select."""
+    import re
+    import numpy as np
+    src = open(os.path.join(ROOT, "polardecoding_b200", "csrc", "polar_common.cuh")).read()
+    body = src[src.index("__device__ __forceinline__ float tbl8<float>(float a)"):src.index("tbl8_select_f32")]
+    incs = [np.uint32(int(h, 16)).view(np.float32) for h in re.findall(r"__int_as_float\((0x[0-9a-f]+)\)", body)]
+    thr = [float(t) for t in re.findall(r"NB, ([0-9.]+)f \*", body)]
+    assert thr == [4.5, 2.252, 1.508, 1.05, 0.71, 0.433, 0.196] and len(incs) == 7
+    lits = [np.float32(v) for v in (0.05, 0.15, 0.25, 0.35, 0.45, 0.55, 0.65)]
+    acc = np.float32(0)
+    for inc, lit in zip(incs, lits):
+        acc = np.float32(acc + inc)          # fmaf(1.0f, inc, acc) rounds once, like this add
+        assert acc == lit, (acc, lit)

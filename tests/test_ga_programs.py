@@ -20,3 +20,21 @@ def test_ga_program_reproduces_reference_table(prog):
     want = open(os.path.join(ROOT, "tests", "golden", "ga_%s.txt" % prog), "rb").read()
     assert out == want
     assert hashlib.md5(out).hexdigest().startswith(MD5[prog])
+
+
+@pytest.mark.parametrize("prog", ["BPRGA_128_W", "BPRGA_128_M", "BPRGA_1024_W"])
+def test_matrix_ga_program_reproduces_reference_table(prog):
+    """the three programs that read the M matrices on stdin: same stdin format as the reference, same stdout"""
+    host = os.path.join(ROOT, "polardecoding_b200", "host")
+    exe = os.path.join(BIN, prog)
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", host, "bin/" + prog], stdout=subprocess.DEVNULL)
+    m = subprocess.run([exe, "--emit-m"], capture_output=True, timeout=120).stdout
+    n, N = (10, 1024) if "1024" in prog else (7, 128)
+    head = m.decode().split("\n")[:n]
+    assert all(len(row.split()) == N for row in head)                        # n rows of N column weights first
+    assert head[0].split()[:4] == ["2", "2", "2", "2"] and head[0].split()[N // 2] == "1"
+    out = subprocess.run([exe], input=m, capture_output=True, timeout=300).stdout
+    assert out == open(os.path.join(ROOT, "tests", "golden", "ga_%s.txt" % prog), "rb").read()
+    bad = subprocess.run([exe], stdin=subprocess.DEVNULL, capture_output=True, timeout=60)
+    assert bad.returncode == 2 and b"stdin" in bad.stderr

@@ -97,6 +97,14 @@ kat["K_BPr_128"] = {"seed": 945, "ebn0": [1.0, 1.5], "stdout": "\n".join(r.stdou
 for prog in ("BPDEGA_128", "BPRGA_128", "BPRGA_1024", "BPRGA_128_allbit"):
     out = subprocess.run([os.path.join(REF_DIR, prog)], stdin=subprocess.DEVNULL, capture_output=True, timeout=120).stdout
     open(os.path.join(OUT, "ga_%s.txt" % prog), "wb").write(out)
+# the three matrix programs read M128.dat / M1024.dat on stdin; the author's files are not in the repository, the closed form
+#  is emitted by the host port's --emit-m and fed to the REFERENCE binaries here
+HOSTBIN = os.path.join(ROOT, "polardecoding_b200", "host", "bin")
+subprocess.check_call(["make", "-C", os.path.join(ROOT, "polardecoding_b200", "host"), "bin/BPRGA_128_W", "bin/BPRGA_1024_W"], stdout=subprocess.DEVNULL)
+for prog in ("BPRGA_128_W", "BPRGA_128_M", "BPRGA_1024_W"):
+    m = subprocess.run([os.path.join(HOSTBIN, "BPRGA_1024_W" if "1024" in prog else "BPRGA_128_W"), "--emit-m"], capture_output=True).stdout
+    out = subprocess.run([os.path.join(REF_DIR, prog)], input=m, capture_output=True, timeout=300).stdout
+    open(os.path.join(OUT, "ga_%s.txt" % prog), "wb").write(out)
 # the author's captures, for cross-checking the three above against the shipped result files
 cap = {}
 with zipfile.ZipFile("/root/reference/myResult_128.zip") as z:
