@@ -88,7 +88,7 @@ __device__ __forceinline__ vec4<real> f4(const vec4<real> &x, const vec4<real> &
 {
     vec4<real> o;
 #pragma unroll
-    for (int e = 0; e < 4; e++) o.v[e] = chk<real>(x.v[e], y.v[e]);
+    for (int e = 0; e < 4; e++) o.v[e] = chk_lean<real>(x.v[e], y.v[e]);
     return o;
 }
 template <typename real>
@@ -350,13 +350,13 @@ __global__ void __launch_bounds__(32) list_decode_kernel(const ListArgs a)
                 real lam;
                 if (!(i & 1)) {
                     if (i == 0) {  // f at stage 1
-                        s1[0] = chk<real>(s2[0], s2[2]);
-                        s1[1] = chk<real>(s2[1], s2[3]);
+                        s1[0] = chk_lean<real>(s2[0], s2[2]);
+                        s1[1] = chk_lean<real>(s2[1], s2[3]);
                     } else {       // g at stage 1, partial sums (u0^u1, u1)
                         s1[0] = s2[2] + RT::flip(s2[0], (ug ^ (ug >> 1)) & 1u);
                         s1[1] = s2[3] + RT::flip(s2[1], (ug >> 1) & 1u);
                     }
-                    lam = chk<real>(s1[0], s1[1]);                              // f at stage 0
+                    lam = chk_lean<real>(s1[0], s1[1]);                              // f at stage 0
                 } else {
                     lam = s1[1] + RT::flip(s1[0], (ug >> (i - 1)) & 1u);        // g at stage 0
                 }

@@ -99,6 +99,38 @@ __device__ __forceinline__ real chk(real a, real b)
     return real_traits<real>::xsign(m, a, b) + delta;
 }
 
+// fp32 CHK with the two table sums accumulated together by packed fp32x2 FMAs (Blackwell FFMA2): 27 instead of 34 issue
+// slots, bit-identical results.  FFMA2 costs ~2.5 FFMA pipe slots (tools/ubench/chk_variants.cu, V7), so this only pays
+// where the issue rate, not the FMA pipe, is the limit: the list decoder gains 5 %, BP (FMA-pipe heavy) loses 2 % -- so
+// list_decode.cu uses chk_lean, bp_decode.cu uses chk.
+__device__ __forceinline__ unsigned long long pk2(float lo, float hi)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+template <typename real>
+__device__ __forceinline__ real chk_lean(real a, real b) { return chk<real>(a, b); }
+template <>
+__device__ __forceinline__ float chk_lean<float>(float a, float b)
+{
+    const float NB = -1.152921504606846976e18f, B = 1.152921504606846976e18f;
+    const float s = fabsf(a + b), d = fabsf(a - b);
+    unsigned long long acc, t;
+#define POLAR_ST(x, T) __saturatef(fmaf(x, NB, T * B))
+#define POLAR_STEP(T, H) t = pk2(POLAR_ST(s, T), POLAR_ST(d, T)); asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(t), "l"(pk2(__int_as_float(H), __int_as_float(H))));
+    t = pk2(POLAR_ST(s, 4.5f), POLAR_ST(d, 4.5f));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(acc) : "l"(t), "l"(pk2(__int_as_float(0x3d4ccccd), __int_as_float(0x3d4ccccd))));
+    POLAR_STEP(2.252f, 0x3dccccce) POLAR_STEP(1.508f, 0x3dcccccc) POLAR_STEP(1.05f, 0x3dcccccc)
+    POLAR_STEP(0.71f, 0x3dcccccc) POLAR_STEP(0.433f, 0x3dccccd0) POLAR_STEP(0.196f, 0x3dccccc8)
+#undef POLAR_STEP
+#undef POLAR_ST
+    float ts, td;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(ts), "=f"(td) : "l"(acc));
+    const float m = fminf(fabsf(a), fabsf(b));
+    return real_traits<float>::xsign(m, a, b) + (ts - td);
+}
+
 // ---------------------------------------------------------------- Philox4x32-10 (counter based)
 struct philox4 { uint32_t x, y, z, w; };
 

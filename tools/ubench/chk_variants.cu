@@ -88,6 +88,45 @@ __device__ __forceinline__ float chk_v5(float a, float b)
     return fmaf(m, 0.05f, xsgn(fminf(fabsf(a), fabsf(b)), a, b));
 }
 
+// V7: steps as scalar FFMA.SAT, the two table sums accumulated together with packed fp32x2 FMAs (Blackwell FFMA2)
+__device__ __forceinline__ unsigned long long pk(float lo, float hi)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c)
+{
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b)
+{
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float chk_v7(float a, float b)
+{
+    const float NB = -1.152921504606846976e18f, B = 1.152921504606846976e18f;
+    const float s = fabsf(a + b), d = fabsf(a - b);
+#define ST(x, T) __saturatef(fmaf(x, NB, T * B))
+#define INC(h) pk(__int_as_float(h), __int_as_float(h))
+    unsigned long long acc = mul2(pk(ST(s, 4.5f), ST(d, 4.5f)), INC(0x3d4ccccd));
+    acc = fma2(pk(ST(s, 2.252f), ST(d, 2.252f)), INC(0x3dccccce), acc);
+    acc = fma2(pk(ST(s, 1.508f), ST(d, 1.508f)), INC(0x3dcccccc), acc);
+    acc = fma2(pk(ST(s, 1.05f), ST(d, 1.05f)), INC(0x3dcccccc), acc);
+    acc = fma2(pk(ST(s, 0.71f), ST(d, 0.71f)), INC(0x3dcccccc), acc);
+    acc = fma2(pk(ST(s, 0.433f), ST(d, 0.433f)), INC(0x3dccccd0), acc);
+    acc = fma2(pk(ST(s, 0.196f), ST(d, 0.196f)), INC(0x3dccccc8), acc);
+#undef ST
+#undef INC
+    float ts, td;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(ts), "=f"(td) : "l"(acc));
+    return xsgn(fminf(fabsf(a), fabsf(b)), a, b) + (ts - td);
+}
+
 template <int V> __device__ __forceinline__ float chkv(float a, float b)
 {
     if (V == 0) return chk_v0(a, b);
@@ -96,6 +135,7 @@ template <int V> __device__ __forceinline__ float chkv(float a, float b)
     if (V == 3) return chk_v3(a, b);
     if (V == 4) return chk_v4(a, b);
     if (V == 6) return chk_v6(a, b);
+    if (V == 7) return chk_v7(a, b);
     return chk_v5(a, b);
 }
 
@@ -164,6 +204,7 @@ int main()
     run<4, 1>(din, dout, "V4 FMA.SAT shared acc"); run<4, 4>(din, dout, "V4 FMA.SAT shared acc");
     run<5, 4>(din, dout, "V5 half2 (inexact)");
     run<6, 1>(din, dout, "V6 shipped (FMA, exact)"); run<6, 2>(din, dout, "V6 shipped (FMA, exact)"); run<6, 4>(din, dout, "V6 shipped (FMA, exact)");
+    run<7, 1>(din, dout, "V7 FFMA2 accumulate (exact)"); run<7, 2>(din, dout, "V7 FFMA2 accumulate (exact)"); run<7, 4>(din, dout, "V7 FFMA2 accumulate (exact)");
     cudaError_t e = cudaDeviceSynchronize();
     printf("%s\n", cudaGetErrorString(e));
     return 0;
