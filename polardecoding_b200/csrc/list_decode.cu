@@ -479,10 +479,10 @@ __global__ void __launch_bounds__(32) list_decode_kernel(const ListArgs a)
 template <typename real, int LOGN, int L>
 struct ListDispatch {
 #ifndef POLAR_SMEM_TOP
-#define POLAR_SMEM_TOP 6
+#define POLAR_SMEM_TOP 5
 #endif
 #ifndef POLAR_BITS_TOP
-#define POLAR_BITS_TOP 8
+#define POLAR_BITS_TOP 7
 #endif
     static constexpr int SMEM_TOP = POLAR_SMEM_TOP, BITS_TOP = POLAR_BITS_TOP;
     using C = ListCfg<real, LOGN, L, SMEM_TOP, BITS_TOP>;
