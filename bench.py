@@ -29,7 +29,7 @@ N, K_INFO = 1024, 512
 OPS_CASCL = 30016 * 27 + 35906 * 2 + 11185 * 11 + 533 * 160 + 36000 + 28000   # ~1.15 M lane-ops / frame
 OPS_BP_SWEEP = 573440                                                          # per sweep, N=1024
 EBN0_CASCL, EBN0_BP = 2.0, 2.5
-B_CASCL, B_BP = 1 << 16, 1 << 15                                               # target frames per step (~256 MB / 128 MB of fp32 LLRs), rounded to whole waves
+B_CASCL, B_BP = 1 << 17, 1 << 15                                               # target frames per step (~512 MB / 128 MB of fp32 LLRs), rounded to whole waves
 
 
 def peaks():

@@ -297,8 +297,11 @@ extern "C" int pg_create(const pg_params *p, pg_ctx **out)
         if (lp.scratch_per_cta) CUC(cudaMalloc(&ctx->d_scratch, lp.scratch_per_cta * (size_t)ctx->grid));
     }
     {
+        // frames per launch: about 2^27 LLRs, rounded to whole waves of the decode kernel so that no SM idles at the end of a launch
         const char *env = getenv("POLARGPU_CHUNK");
-        size_t c = env ? (size_t)atoll(env) : ((size_t)1 << 26) / (size_t)p->N;
+        size_t c = env ? (size_t)atoll(env) : ((size_t)1 << 27) / (size_t)p->N;
+        const size_t wave = (size_t)ctx->grid * ((p->decoder == PG_DEC_BP) ? 1 : (size_t)(32 / L));
+        if (!env && wave > 0) c = std::max<size_t>(1, c / wave) * wave;
         ctx->chunk_max = std::max<size_t>(c, 32);
     }
 #undef CUC
