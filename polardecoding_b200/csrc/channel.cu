@@ -63,25 +63,29 @@ __global__ void __launch_bounds__(128) channel_kernel(const ChannelArgs a, const
         if (a.r == 0) {
             wv = v;
         } else if (!a.crc_systematic) {
-            // w(D) = v(D) g(D): w_i = XOR_e g_e v_{i-e}  (CASCL_1024_L8.c:251-266)
-            for (int b = 0; b < 32; b++) {
-                const int i = 32 * wl + b;
-                uint32_t acc = 0;
-                if (i < a.nI)
-                    for (int e = 0; e <= a.r; e++)
-                        if ((a.crc_poly >> e) & 1ull) acc ^= vbit(i - e);
-                wv |= acc << b;
+            // w(D) = v(D) g(D): w = XOR over the taps e of (v << e), on packed words  (CASCL_1024_L8.c:251-266)
+            for (int e = 0; e <= a.r; e++) {
+                if (!((a.crc_poly >> e) & 1ull)) continue;
+                const int ws = e >> 5, bs = e & 31;          // word and bit part of the shift
+                const int src = wl - ws;
+                uint32_t lo = (src >= 0 && src < W) ? vf[src] : 0u;
+                uint32_t hi = (src - 1 >= 0 && src - 1 < W) ? vf[src - 1] : 0u;
+                wv ^= bs ? ((lo << bs) | (hi >> (32 - bs))) : lo;
             }
+            const int rem = a.nI - 32 * wl;
+            if (rem < 32) wv &= (rem > 0) ? ((1u << rem) - 1u) : 0u;
         } else {
             // parity p(D) = v(D) D^r mod g(D) in w[0..r), payload in w[r..r+K)  (CASCL_1024_sys.c:781-789)
             uint32_t par = 0;
             for (int i = wl; i < a.K; i += W)
                 if (vbit(i)) par ^= __ldg(a.crc_sys + i);
             for (int d = 1; d < W; d <<= 1) par ^= __shfl_xor_sync(0xffffffffu, par, d);
-            for (int b = 0; b < 32; b++) {
-                const int i = 32 * wl + b;
-                const uint32_t bit = (i < a.r) ? ((par >> i) & 1u) : vbit(i - a.r);
-                wv |= bit << b;
+            {   // payload shifted up by r bits, parity in bits 0..r-1 (r <= 32)
+                const int ws = a.r >> 5, bs = a.r & 31, src = wl - ws;
+                const uint32_t lo = (src >= 0 && src < W) ? vf[src] : 0u;
+                const uint32_t hi = (src - 1 >= 0 && src - 1 < W) ? vf[src - 1] : 0u;
+                wv = bs ? ((lo << bs) | (hi >> (32 - bs))) : lo;
+                if (wl == 0) wv |= (a.r == 32) ? par : (par & ((1u << a.r) - 1u));
             }
         }
         ww[lane] = wv;
