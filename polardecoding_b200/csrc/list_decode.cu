@@ -186,11 +186,12 @@ __global__ void __launch_bounds__(32) list_decode_kernel(const ListArgs a)
                 // scratch / channel operands come from L2 or HBM: fetch the next pair while the current four CHKs run
                 V4 x = ldv(src), y = ldv(src2);
 #pragma unroll 1
-                for (int i4 = 0; i4 < cnt4; i4++, dst += 32) {
-                    V4 nx = x, ny = y;
-                    if (i4 + 1 < cnt4) { src += stride; src2 += stride; nx = ldv(src); ny = ldv(src2); }
+                for (int i4 = 0; i4 < cnt4; i4 += 2, dst += 64) {  // cnt4 >= 8 here; two steps per trip so that the operand
+                    src += stride; src2 += stride;                 // registers ping-pong instead of being copied
+                    const V4 x1 = ldv(src), y1 = ldv(src2);
                     stv(dst, f4<real>(x, y));
-                    x = nx; y = ny;
+                    if (i4 + 2 < cnt4) { src += stride; src2 += stride; x = ldv(src); y = ldv(src2); }
+                    stv(dst + 32, f4<real>(x1, y1));
                 }
             }
             set_pfield(s);
