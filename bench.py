@@ -144,9 +144,11 @@ def run_reference_arm(a):
 
 
 # ------------------------------------------------------------------ GPU arm
-def timed_steps(torch, dist, world, ext_stream, fn, steps, warmup):
+def timed_steps(torch, dist, world, ext_stream, fn, steps, warmup, count=None):
     for _ in range(warmup):
         fn()
+    if count:
+        count("start")
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -157,6 +159,8 @@ def timed_steps(torch, dist, world, ext_stream, fn, steps, warmup):
         fn()
     e1.record(ext_stream)
     torch.cuda.synchronize()
+    if count:
+        count("stop")
     ms = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([ms], device="cuda")
@@ -166,9 +170,11 @@ def timed_steps(torch, dist, world, ext_stream, fn, steps, warmup):
     return ms
 
 
-def wall_steps(torch, dist, world, fn, steps, warmup):
+def wall_steps(torch, dist, world, fn, steps, warmup, count=None):
     for _ in range(warmup):
         fn()
+    if count:
+        count("start")
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -176,6 +182,8 @@ def wall_steps(torch, dist, world, fn, steps, warmup):
     for _ in range(steps):
         fn()
     torch.cuda.synchronize()
+    if count:
+        count("stop")
     ms = (time.perf_counter() - t0) * 1e3
     if world > 1:
         t = torch.tensor([ms], device="cuda")
@@ -225,13 +233,19 @@ def run_gpu_arm(a):
         first = (1 << 32) + rank * B                                  # disjoint Philox frame ranges per rank
         eng.channel_device(ebn0, first, B, llr.data_ptr(), truth.data_ptr())
         eng.sync()
-        l0 = eng.launches()
+        mark = [0]
+
+        def count(what):  # kernels of this library launched inside the timed regions only
+            nonlocal launches
+            if what == "start":
+                mark[0] = eng.launches()
+            else:
+                launches += eng.launches() - mark[0]
         eng.counters_read(reset=True)
-        ms = timed_steps(torch, dist, world, st, lambda: eng.decode_count_device(llr.data_ptr(), B, truth.data_ptr(), None, info.data_ptr()), a.steps, a.warmup)
+        ms = timed_steps(torch, dist, world, st, lambda: eng.decode_count_device(llr.data_ptr(), B, truth.data_ptr(), None, info.data_ptr()), a.steps, a.warmup, count)
         cnt = eng.counters_read(reset=True)
         if world > 1:
             cnt = eng.allreduce_counters(cnt)                          # the one collective of the path: final counters
-        launches += eng.launches() - l0
         per_step = ms / a.steps
         fps = world * B / (per_step * 1e-3)
         steps_total = a.steps + a.warmup
@@ -259,9 +273,7 @@ def run_gpu_arm(a):
         h_llr.copy_(llr[: Be * N])
         h_out = torch.empty(Be * (N // 32), dtype=torch.int32).pin_memory()
         h_flags = torch.empty(Be, dtype=torch.int32).pin_memory()
-        l0 = eng.launches()
-        ms_e = wall_steps(torch, dist, world, lambda: eng.decode_llr_host_ptr(h_llr.data_ptr(), False, Be, h_out.data_ptr(), h_flags.data_ptr()), a.steps, max(1, a.warmup))
-        launches += eng.launches() - l0
+        ms_e = wall_steps(torch, dist, world, lambda: eng.decode_llr_host_ptr(h_llr.data_ptr(), False, Be, h_out.data_ptr(), h_flags.data_ptr()), a.steps, max(1, a.warmup), count)
         fps_e = world * Be / (ms_e / a.steps * 1e-3)
         out["e2e"] = {"value": fps_e * K_INFO / 1e9, "unit": "Gbit/s", "h2d_bytes_per_step": Be * N * 4, "d2h_bytes_per_step": Be * (N // 8) + Be * 4,
                       "frames_per_s": fps_e, "frames_per_step": world * Be}
