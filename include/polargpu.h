@@ -47,7 +47,9 @@ enum pg_status {
 
 enum pg_decoder { PG_DEC_SC = 0, PG_DEC_SCL = 1, PG_DEC_CASCL = 2, PG_DEC_BP = 3 };
 enum pg_real { PG_REAL_F64 = 0, /* parity mode: bit-exact with the reference's double arithmetic */
-               PG_REAL_F32 = 1  /* throughput mode */ };
+               PG_REAL_F32 = 1, /* throughput mode */
+               PG_REAL_H2 = 2   /* BP only, optional: messages as packed half (two frames per __half2); a numerically
+                                   different decoder, judged on FER only; LLR buffers stay float */ };
 enum pg_data { PG_DATA_PN63 = 0,  /* the reference's PN-63 payload, phase m = frame*(K%63) mod 63 (SC_128.c:126-138,180,214) */
                PG_DATA_PHILOX = 1 /* random payload from the Philox stream */ };
 

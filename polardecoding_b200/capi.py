@@ -12,7 +12,7 @@ PROGRAMS = ["SC_128", "SC_1024", "SC_128_fag", "SCL_128", "SCL_1024", "SCL_128_f
             "CASCL_1024_sys", "BP_128", "BP_1024", "BP_128_fag", "BPr_128"]
 
 PG_DEC_SC, PG_DEC_SCL, PG_DEC_CASCL, PG_DEC_BP = 0, 1, 2, 3
-PG_REAL_F64, PG_REAL_F32 = 0, 1
+PG_REAL_F64, PG_REAL_F32, PG_REAL_H2 = 0, 1, 2
 PG_DATA_PN63, PG_DATA_PHILOX = 0, 1
 
 
@@ -97,7 +97,7 @@ class Engine:
         p = params if params is not None else preset(program)
         for k, v in over.items():
             if k == "real":
-                v = {"f64": PG_REAL_F64, "f32": PG_REAL_F32}.get(v, v)
+                v = {"f64": PG_REAL_F64, "f32": PG_REAL_F32, "h2": PG_REAL_H2}.get(v, v)
             setattr(p, k, v)
         self.params = p
         self.ctx = C.c_void_p()

@@ -57,6 +57,7 @@ struct pg_ctx {
     pg_params p;
     int n = 0, W = 0, nI = 0;
     bool f64 = false;
+    bool h2 = false;           // BP with packed-half messages (PG_REAL_H2); device LLRs are float
     int sm_count = 0;
     std::vector<int> I;
     std::vector<uint8_t> inI;
@@ -212,7 +213,8 @@ extern "C" int pg_create(const pg_params *p, pg_ctx **out)
     if (p->K < 1 || p->crc_bits < 0 || p->crc_bits > 32 || p->K + p->crc_bits > p->N) return fail(PG_ERR_ARG, "bad K / crc_bits");
     if (p->crc_bits > 0 && (((p->crc_poly >> p->crc_bits) & 1ull) == 0 || (p->crc_poly & 1ull) == 0)) return fail(PG_ERR_ARG, "crc_poly must contain D^r and 1");
     if (p->decoder < PG_DEC_SC || p->decoder > PG_DEC_BP) return fail(PG_ERR_ARG, "bad decoder");
-    if (p->real != PG_REAL_F64 && p->real != PG_REAL_F32) return fail(PG_ERR_ARG, "bad real");
+    if (p->real != PG_REAL_F64 && p->real != PG_REAL_F32 && p->real != PG_REAL_H2) return fail(PG_ERR_ARG, "bad real");
+    if (p->real == PG_REAL_H2 && p->decoder != PG_DEC_BP) return fail(PG_ERR_UNSUPPORTED, "PG_REAL_H2 is a BP-only mode");
     if (p->nranks < 1 || p->rank < 0 || p->rank >= p->nranks) return fail(PG_ERR_ARG, "bad rank/nranks");
     const int L = (p->decoder == PG_DEC_SC) ? 1 : p->list_size;
     if (p->decoder != PG_DEC_BP && (L < 1 || L > 32 || (L & (L - 1)))) return fail(PG_ERR_ARG, "list_size must be 1,2,4,8,16,32");
@@ -233,6 +235,7 @@ extern "C" int pg_create(const pg_params *p, pg_ctx **out)
     ctx->p = *p;
     ctx->p.list_size = L;
     ctx->f64 = (p->real == PG_REAL_F64);
+    ctx->h2 = (p->real == PG_REAL_H2);
     ctx->sm_count = prop.multiProcessorCount;
     build_code(ctx);
     auto bail = [&](int code) { g_create_error = ctx->err; pg_destroy(ctx); return code; };
@@ -282,7 +285,7 @@ extern "C" int pg_create(const pg_params *p, pg_ctx **out)
     // launch geometry
     if (p->decoder == PG_DEC_BP) {
         BpPlan bp;
-        cudaError_t pe = bp_plan(ctx->n, ctx->f64, &bp);
+        cudaError_t pe = ctx->h2 ? bp_h2_plan(ctx->n, &bp) : bp_plan(ctx->n, ctx->f64, &bp);
         if (pe != cudaSuccess) { ctx->err = std::string("no BP kernel for this N: ") + cudaGetErrorString(pe); return bail(PG_ERR_UNSUPPORTED); }
         if (bp.ctas_per_sm < 1) { ctx->err = "BP kernel does not fit on an SM"; return bail(PG_ERR_UNSUPPORTED); }
         ctx->grid = ctx->sm_count * bp.ctas_per_sm;
@@ -300,7 +303,7 @@ extern "C" int pg_create(const pg_params *p, pg_ctx **out)
         // frames per launch: about 2^27 LLRs, rounded to whole waves of the decode kernel so that no SM idles at the end of a launch
         const char *env = getenv("POLARGPU_CHUNK");
         size_t c = env ? (size_t)atoll(env) : ((size_t)1 << 27) / (size_t)p->N;
-        const size_t wave = (size_t)ctx->grid * ((p->decoder == PG_DEC_BP) ? 1 : (size_t)(32 / L));
+        const size_t wave = (size_t)ctx->grid * ((p->decoder == PG_DEC_BP) ? (ctx->h2 ? 2 : 1) : (size_t)(32 / L));
         if (!env && wave > 0) c = std::max<size_t>(1, c / wave) * wave;
         ctx->chunk_max = std::max<size_t>(c, 32);
     }
@@ -396,8 +399,14 @@ static int run_decode(pg_ctx *ctx, const void *d_llr, size_t B, const uint32_t *
         a.B = B; a.iters = p.iter_max; a.early_stop = p.bp_early_stop;
         a.m = ctx->masks;
         CU(cudaMemsetAsync(ctx->d_queue, 0, 8, ctx->st));
-        const int grid = (int)std::min<size_t>((size_t)ctx->grid, B);
-        CU(launch_bp(a, ctx->n, ctx->f64, std::max(grid, 1), ctx->st));
+        if (ctx->h2) {
+            if (a.bpr_E) { ctx->err = "the BPR statistic is not available in PG_REAL_H2 mode"; return PG_ERR_UNSUPPORTED; }
+            const int grid = (int)std::min<size_t>((size_t)ctx->grid, (B + 1) / 2);
+            CU(launch_bp_h2(a, ctx->n, std::max(grid, 1), ctx->st));
+        } else {
+            const int grid = (int)std::min<size_t>((size_t)ctx->grid, B);
+            CU(launch_bp(a, ctx->n, ctx->f64, std::max(grid, 1), ctx->st));
+        }
     } else {
         ListArgs a;
         std::memset(&a, 0, sizeof(a));
@@ -470,7 +479,7 @@ extern "C" int pg_channel_device(pg_ctx *ctx, double ebn0_db, uint64_t first_fra
 
 static uint64_t wave_frames(const pg_ctx *ctx)
 {
-    const uint64_t per_cta = (ctx->p.decoder == PG_DEC_BP) ? 1 : (uint64_t)(32 / ctx->p.list_size);
+    const uint64_t per_cta = (ctx->p.decoder == PG_DEC_BP) ? (ctx->h2 ? 2 : 1) : (uint64_t)(32 / ctx->p.list_size);
     return (uint64_t)ctx->grid * per_cta;
 }
 

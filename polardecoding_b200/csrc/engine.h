@@ -74,6 +74,9 @@ struct BpArgs {
 struct BpPlan { size_t smem; int ctas_per_sm; int threads; };
 cudaError_t bp_plan(int n, bool f64, BpPlan *plan);
 cudaError_t launch_bp(const BpArgs &a, int n, bool f64, int grid, cudaStream_t st);
+// packed-half variant (two frames per CTA, float LLRs in; no BPR statistic)
+cudaError_t bp_h2_plan(int n, BpPlan *plan);
+cudaError_t launch_bp_h2(const BpArgs &a, int n, int grid, cudaStream_t st);
 
 // ---------------------------------------------------------------- helpers
 cudaError_t launch_convert_llr(const void *src, bool src_f64, void *dst, bool dst_f64, size_t count, cudaStream_t st);

@@ -321,7 +321,7 @@ int main(int argc, char **argv)
         else if (!strcmp(a, "--max-frames") && v) { maxf = atoll(v); i++; }
         else if (!strcmp(a, "--seed") && v) { seed = atoll(v); i++; }
         else if (!strcmp(a, "--rng") && v) { use_ref = !strcmp(v, "ref"); i++; }
-        else if (!strcmp(a, "--real") && v) { real = !strcmp(v, "f64") ? PG_REAL_F64 : PG_REAL_F32; i++; }
+        else if (!strcmp(a, "--real") && v) { real = !strcmp(v, "f64") ? PG_REAL_F64 : (!strcmp(v, "h2") ? PG_REAL_H2 : PG_REAL_F32); i++; }
         else if (!strcmp(a, "--L") && v) { L = atol(v); i++; }
         else if (!strcmp(a, "--iters") && v) { iters = atol(v); i++; }
         else if (!strcmp(a, "--gpus") && v) { gpus = atol(v); i++; }

@@ -191,3 +191,26 @@ def test_fp32_flip_rate_is_below_the_north_star_bar():
     print("CA-SCL 1024 L=8 at 1.5 dB: %d of %d frames differ between fp32 and fp64" % (diff, B))
     assert diff <= 12          # 1e-4 of 60 000 = 6 expected at the bar; measured ~2; allow Poisson spread
     e32.close(); e64.close()
+
+
+@pytest.mark.parametrize("prog,B,ebn0", [("BP_1024", 4096, 2.5), ("BP_128", 20000, 3.0)])
+def test_bp_half2_mode_fer(prog, B, ebn0):
+    """PG_REAL_H2 (optional flag, north_star item 4): packed-half BP is a numerically different decoder, so it is
+    judged on FER only: same frames through the f32 and the h2 contexts, block error rates within a 95 % interval."""
+    from polardecoding_b200 import Engine
+    e32 = Engine(prog, real="f32", seed=7, data_mode=1)
+    eh2 = Engine(prog, real="h2", seed=7, data_mode=1)
+    assert eh2.wave_frames() % 2 == 0
+    a32, _ = e32.simulate_batch(ebn0, 0, B)
+    ah2, fe = eh2.simulate_batch(ebn0, 0, B + 1, want_frame_err=True)   # odd batch: the last pair holds one frame
+    assert ah2.frames == B + 1 and a32.frames == B
+    p32, ph2 = a32.err_blocks / B, ah2.err_blocks / (B + 1)
+    assert int((fe > 0).sum()) == ah2.err_blocks
+    ci = 1.96 * np.sqrt(max(p32, 1.0 / B) * (1 - p32) * 2 / B)
+    print("%s at %.1f dB: FER f32 %.5f, h2 %.5f (95%% half-width %.5f)" % (prog, ebn0, p32, ph2, ci))
+    assert ph2 <= p32 + 2 * ci + 2.0 / B
+    # streaming call: decisions of the same LLRs equal the simulate path's error pattern
+    llr, u = eh2.channel(ebn0, 0, 64)
+    got, flags = eh2.decode_llr(llr)
+    assert (((got != u) & (eh2.inI[None, :] > 0)).sum(1) == fe[:64]).all()
+    e32.close(); eh2.close()
