@@ -49,9 +49,11 @@ struct ListCfg {
     static constexpr int TOP = (SMEM_TOP < LOGN) ? SMEM_TOP : LOGN;            // LLR stages 2..TOP-1 in smem
     static constexpr int BTOP = (BITS_TOP < LOGN + 1) ? BITS_TOP : LOGN + 1;    // bit stages 6..BTOP-1 in smem
     static constexpr int BLO = (BTOP > 6) ? BTOP : 6;                           // first bit stage in global scratch
-    static constexpr int SM_STAGE_REALS = 32 * ((1 << TOP) - 4);
+    static constexpr int SM_STAGE_REALS = 32 * ((1 << TOP) - 8);          // stages 3..TOP-1 (stage 2 lives in registers only)
+    static_assert(SMEM_TOP >= 4, "stage 3 is always in shared memory");
     static constexpr int SM_BIT_WORDS = (BTOP > 6) ? 32 * ((1 << (BTOP - 5)) - 2) : 0;
-    static constexpr size_t SMEM = (size_t)SM_STAGE_REALS * sizeof(real) + (size_t)SM_BIT_WORDS * 4;
+    static constexpr int SM_SLOT_WORDS = (L > 1) ? 32 : 0;                      // clone-source table, one word per lane
+    static constexpr size_t SMEM = (size_t)SM_STAGE_REALS * sizeof(real) + (size_t)SM_BIT_WORDS * 4 + (size_t)SM_SLOT_WORDS * 4;
     static constexpr size_t GS_REALS = 32 * (size_t)((1 << LOGN) - (1 << TOP));                    // stages TOP..LOGN-1
     static constexpr size_t GS_BIT_WORDS = (LOGN >= BLO) ? 32 * (size_t)((1 << (LOGN - 4)) - (1 << (BLO - 5))) : 0;  // BLO..LOGN
     static constexpr size_t GS_BYTES = GS_REALS * sizeof(real) + GS_BIT_WORDS * 4;
@@ -82,6 +84,32 @@ __device__ __forceinline__ void stv(vec4<double> *p, const vec4<double> &o)
 __device__ __forceinline__ float rmax(float a, float b) { return fmaxf(a, b); }
 __device__ __forceinline__ double rmax(double a, double b) { return fmax(a, b); }
 
+// lo <- max of lo, hi <- min of hi over the L lanes of a frame (mask = those lanes).  Path metrics are non-negative (or +inf), so
+// in fp32 their bit patterns order like unsigned integers and one REDUX per value replaces log2(L) shuffle + min/max steps.
+template <int L>
+__device__ __forceinline__ void frame_minmax(float &lo, float &hi, uint32_t mask)
+{
+#ifdef POLAR_REDUX
+    lo = __uint_as_float(__reduce_max_sync(mask, __float_as_uint(lo)));
+    hi = __uint_as_float(__reduce_min_sync(mask, __float_as_uint(hi)));
+#else
+#pragma unroll
+    for (int d = 1; d < L; d <<= 1) {
+        lo = fmaxf(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+        hi = fminf(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+    }
+#endif
+}
+template <int L>
+__device__ __forceinline__ void frame_minmax(double &lo, double &hi, uint32_t)
+{
+#pragma unroll
+    for (int d = 1; d < L; d <<= 1) {
+        lo = fmax(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+        hi = fmin(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+    }
+}
+
 // one CHK / g evaluation of four neighbouring nodes
 template <typename real>
 __device__ __forceinline__ vec4<real> f4(const vec4<real> &x, const vec4<real> &y)
@@ -101,7 +129,7 @@ __device__ __forceinline__ vec4<real> g4(const vec4<real> &up, const vec4<real> 
 }
 
 template <typename real, int LOGN, int L, int SMEM_TOP, int BITS_TOP>
-__global__ void __launch_bounds__(32) list_decode_kernel(const ListArgs a)
+__global__ void __launch_bounds__(32, (sizeof(real) == 4) ? 32 : 16) list_decode_kernel(const ListArgs a)
 {
     using C = ListCfg<real, LOGN, L, SMEM_TOP, BITS_TOP>;
     using RT = real_traits<real>;
@@ -115,8 +143,9 @@ __global__ void __launch_bounds__(32) list_decode_kernel(const ListArgs a)
     const real INF = RT::inf();
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    V4 *const sm_stage = reinterpret_cast<V4 *>(smem_raw);  // stage s (2<=s<TOP): group i4 of lane pl at [8*(2^s-4) + i4*32 + pl]
+    V4 *const sm_stage = reinterpret_cast<V4 *>(smem_raw);  // stage s (3<=s<TOP): group i4 of lane pl at [8*(2^s-8) + i4*32 + pl]
     uint32_t *const sm_bits = reinterpret_cast<uint32_t *>(smem_raw + (size_t)C::SM_STAGE_REALS * sizeof(real));
+    uint32_t *const sm_slot = sm_bits + C::SM_BIT_WORDS;  // [32]: lane id of the t-th both-survivor of each frame
     unsigned char *const gs_raw = reinterpret_cast<unsigned char *>(a.gscratch) + (size_t)blockIdx.x * C::GS_BYTES;
     V4 *const gs_stage = reinterpret_cast<V4 *>(gs_raw);
     uint32_t *const gs_bits = reinterpret_cast<uint32_t *>(gs_raw + C::GS_REALS * sizeof(real));
@@ -126,10 +155,13 @@ __global__ void __launch_bounds__(32) list_decode_kernel(const ListArgs a)
     const int fbase = lane - k;
     const int fl = lane / L;
     const unsigned long long groups = (a.B + FPW - 1) / FPW;
+    ptr_t kpat = 0;  // k in every pointer field
+#pragma unroll
+    for (int i = 0; i * PWID < (int)(8 * sizeof(ptr_t)) - PWID + 1; i++) kpat |= (ptr_t)k << (i * PWID);
 
     // home arrays (generic pointers: one code path for shared and global stages keeps the hot loop small)
     auto stage_at = [&](int s) -> V4 * {
-        return (s < TOP) ? (sm_stage + 8 * ((1 << s) - 4)) : (gs_stage + 8 * (size_t)((1 << s) - (1 << TOP)));
+        return (s < TOP) ? (sm_stage + 8 * ((1 << s) - 8)) : (gs_stage + 8 * (size_t)((1 << s) - (1 << TOP)));
     };
     // bit array of stage s (s>=6): word w of physical lane pl at [w*32 + pl]
     auto bits_at = [&](int s) -> uint32_t * {
@@ -149,19 +181,25 @@ __global__ void __launch_bounds__(32) list_decode_kernel(const ListArgs a)
 
         auto pfield = [&](int s) -> int { return (L == 1) ? 0 : (int)((ptr >> ((s - 2) * PWID)) & PMASK); };
         auto bfield = [&](int s) -> int { return (L == 1) ? 0 : (int)((bptr >> ((s - 6) * PWID)) & PMASK); };
-        auto set_pfield = [&](int s) {
-            if (L > 1) ptr = (ptr & ~(PMASK << ((s - 2) * PWID))) | ((ptr_t)k << ((s - 2) * PWID));
+        // after a chain of layers the stages 3..top live in this lane's home arrays: one masked merge of k into those fields
+        auto set_pfields = [&](int top) {
+            if (L > 1) {
+                const ptr_t fm = (~(ptr_t)0 >> ((int)(8 * sizeof(ptr_t)) - (top - 1) * PWID)) & ~PMASK;
+                ptr = (ptr & ~fm) | (kpat & fm);
+            }
         };
         auto set_bfield = [&](int s) {
             if (L > 1) bptr = (bptr & ~(PMASK << ((s - 6) * PWID))) | ((ptr_t)k << ((s - 6) * PWID));
         };
 
-        // ---- f-layer producing stage s (2 <= s < LOGN) from stage s+1, into the HOME array -----------------
+        // ---- f-layer producing stage s (4 <= s < LOGN) from stage s+1, into the HOME array -----------------
+        // An f-layer always follows the layer that produced stage s+1 in the same chain, so its source is this lane's own
+        // home array (or the channel): no pointer lookup.  Pointer fields are set once per chain (set_pfields).
         auto f_layer = [&](int s, bool coop) {
             const int cnt4 = 1 << (s - 2);
             if (coop) {
                 // all lanes of the frame still hold the same path (no information bit yet): they split the layer and
-                // write ONE array, slot 0's home; every pointer field still says slot 0
+                // write ONE array, slot 0's home; every pointer field of a stage >= 4 still says slot 0
                 V4 *dst = stage_at(s) + fbase;
                 const V4 *src = ch4;
                 int stride = 1;
@@ -171,34 +209,24 @@ __global__ void __launch_bounds__(32) list_decode_kernel(const ListArgs a)
                 __syncwarp();
                 return;
             }
-            if (s + 1 < TOP) {  // shared -> shared (LDS/STS, 32-bit addressing)
-                V4 *dst = sm_stage + 8 * ((1 << s) - 4) + lane;
-                const V4 *src = sm_stage + 8 * ((2 << s) - 4) + fbase + pfield(s + 1);
-                const V4 *src2 = src + cnt4 * 32;
+            V4 *dst = stage_at(s) + lane;
+            const V4 *src = ch4;
+            int stride = 1;
+            if (s + 1 != LOGN) { src = stage_at(s + 1) + lane; stride = 32; }
+            const V4 *src2 = src + cnt4 * stride;
+            // scratch / channel operands come from L2 or HBM: fetch the next pair while the current four CHKs run
+            V4 x = ldv(src), y = ldv(src2);
 #pragma unroll 1
-                for (int i4 = 0; i4 < cnt4; i4++, dst += 32, src += 32, src2 += 32) stv(dst, f4<real>(ldv(src), ldv(src2)));
-            } else {
-                V4 *dst = stage_at(s) + lane;
-                const V4 *src = ch4;
-                int stride = 1;
-                if (s + 1 != LOGN) { src = stage_at(s + 1) + fbase + pfield(s + 1); stride = 32; }
-                const V4 *src2 = src + cnt4 * stride;
-                // scratch / channel operands come from L2 or HBM: fetch the next pair while the current four CHKs run
-                V4 x = ldv(src), y = ldv(src2);
-#pragma unroll 1
-                for (int i4 = 0; i4 < cnt4; i4 += 2, dst += 64) {  // cnt4 >= 8 here; two steps per trip so that the operand
-                    src += stride; src2 += stride;                 // registers ping-pong instead of being copied
-                    const V4 x1 = ldv(src), y1 = ldv(src2);
-                    stv(dst, f4<real>(x, y));
-                    if (i4 + 2 < cnt4) { src += stride; src2 += stride; x = ldv(src); y = ldv(src2); }
-                    stv(dst + 32, f4<real>(x1, y1));
-                }
+            for (int i4 = 0; i4 < cnt4; i4 += 2, dst += 64) {  // cnt4 >= 4 here; two steps per trip so that the operand
+                src += stride; src2 += stride;                 // registers ping-pong instead of being copied
+                const V4 x1 = ldv(src), y1 = ldv(src2);
+                stv(dst, f4<real>(x, y));
+                if (i4 + 2 < cnt4) { src += stride; src2 += stride; x = ldv(src); y = ldv(src2); }
+                stv(dst + 32, f4<real>(x1, y1));
             }
-            set_pfield(s);
-            __syncwarp();
         };
 
-        // ---- g-layer producing stage t (2 <= t < LOGN) from stage t+1 and the partial sums B[t] ------------
+        // ---- g-layer producing stage t (4 <= t < LOGN) from stage t+1 (via the pointer word) and the partial sums B[t]
         auto g_layer = [&](int t, bool coop) {
             const int cnt4 = 1 << (t - 2);
             if (coop) {  // as above; the partial sums of an all-frozen prefix are zero, so g = lower + upper
@@ -216,34 +244,25 @@ __global__ void __launch_bounds__(32) list_decode_kernel(const ListArgs a)
             int stride = 1;
             if (t + 1 != LOGN) { src = stage_at(t + 1) + fbase + pfield(t + 1); stride = 32; }
             const V4 *src2 = src + cnt4 * stride;
-            if (t < 6) {
-                uint32_t bw = (t == 2) ? (Blow & 0xFu) : (t == 3) ? ((Blow >> 4) & 0xFFu) : (t == 4) ? ((Blow >> 12) & 0xFFFFu) : B5;
+            // a g-layer is one add per node: memory bound (its operands come from the L2/HBM scratch).  Batches of four
+            // node groups: eight independent 128-bit loads in flight per lane, 16 partial-sum bits per batch.
+            const uint32_t *bsrc = (t >= 6) ? bits_at(t) + fbase + bfield(t) : nullptr;
+            uint32_t bw = (t == 4) ? ((Blow >> 12) & 0xFFFFu) : B5;
 #pragma unroll 1
-                for (int i4 = 0; i4 < cnt4; i4++, dst += 32, src += stride, src2 += stride, bw >>= 4) stv(dst, g4<real>(ldv(src), ldv(src2), bw & 0xFu));
-            } else {
-                // a g-layer is one add per node: memory bound.  Eight independent 128-bit loads in flight per lane.
-                const uint32_t *bsrc = bits_at(t) + fbase + bfield(t);
-#pragma unroll 1
-                for (int w = 0; w < (cnt4 >> 3); w++, bsrc += 32) {
-                    uint32_t bw = *bsrc;
-#pragma unroll 1
-                    for (int h = 0; h < 2; h++) {
-                        V4 up[4], lo[4];
+            for (int b = 0; b < (cnt4 >> 2); b++) {
+                if (t >= 6 && !(b & 1)) { bw = *bsrc; bsrc += 32; }
+                V4 up[4], lo[4];
 #pragma unroll
-                        for (int q = 0; q < 4; q++) { up[q] = ldv(src + q * stride); lo[q] = ldv(src2 + q * stride); }
+                for (int q = 0; q < 4; q++) { up[q] = ldv(src + q * stride); lo[q] = ldv(src2 + q * stride); }
 #pragma unroll
-                        for (int q = 0; q < 4; q++) stv(dst + q * 32, g4<real>(up[q], lo[q], (bw >> (4 * q)) & 0xFu));
-                        dst += 4 * 32; src += 4 * stride; src2 += 4 * stride; bw >>= 16;
-                    }
-                }
+                for (int q = 0; q < 4; q++) stv(dst + q * 32, g4<real>(up[q], lo[q], (bw >> (4 * q)) & 0xFu));
+                dst += 4 * 32; src += 4 * stride; src2 += 4 * stride; bw >>= 16;
             }
-            set_pfield(t);
-            __syncwarp();
         };
 
         // ---- one leaf: frozen -> PM only; information -> decide (SC) or fork/prune (list) ------------------
-        auto leaf = [&](int j, real lam) -> uint32_t {
-            const bool info = (a.m.info[j >> 5] >> (j & 31)) & 1u;
+        // first: the even leaf of a pair (its stage-1 values are read again by the odd leaf); keep2: stage 2 is still needed
+        auto leaf = [&](bool info, real lam, bool first, bool keep2) -> uint32_t {
             if (L == 1) return (info && !(lam >= (real)0)) ? 1u : 0u;  // SC_128.c:426-431
             const real ab = rabs(lam);
             const real t = tbl8<real>(ab);
@@ -253,30 +272,45 @@ __global__ void __launch_bounds__(32) list_decode_kernel(const ListArgs a)
                 pm = pm + ((lam < (real)0) ? pen : t);
                 return 0u;
             }
-            const real c0 = pm + ((lam < (real)0) ? pen : t);
-            const real c1 = pm + ((lam > (real)0) ? pen : t);
+            const real cm = pm + t, cM = pm + pen;      // the cheaper and the dearer child of this path (cm <= cM)
+            const real c0 = (lam < (real)0) ? cM : cm;  // bit 0
+            const real c1 = (lam > (real)0) ? cM : cm;  // bit 1
             // The reference keeps the candidates with PM < med, med = (L+1)-th smallest of the 2L (SCL_1024.c:619-633).
-            // med without ranking: sort the bit-0 candidates and the bit-1 candidates across the frame's lanes (bitonic
-            // networks on shuffles), then lo_k = min(a_k, b_{L-1-k}) are the L smallest, so sorted[L-1] = max lo, med = min hi.
-            real sa = c0, sb = c1;
+            // lo = L-th and hi = (L+1)-th smallest from a bitonic merge network over the 2L values laid out as
+            // index = 2*slot + {x, y}: every merge starts with the mirror step (element i against element size-1-i, the
+            // partner lane's OTHER register), steps at distance 1 are in-lane, and the last merge stops after its mirror step:
+            // the lower L elements are then the L smallest, so lo is their maximum and hi the minimum of the upper L.
+            real x = cm, y = cM;
 #pragma unroll
             for (int size = 2; size <= L; size <<= 1) {
+                const bool low = (k & (size >> 1)) == 0;
+                const real ox = __shfl_xor_sync(0xffffffffu, x, size - 1);
+                const real oy = __shfl_xor_sync(0xffffffffu, y, size - 1);
+                x = low ? rmin(x, oy) : rmax(x, oy);
+                y = low ? rmin(y, ox) : rmax(y, ox);
+                if (size < L) {
 #pragma unroll
-                for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                    const real oa = __shfl_xor_sync(0xffffffffu, sa, stride);
-                    const real ob = __shfl_xor_sync(0xffffffffu, sb, stride);
-                    const bool keep_min = (((k & size) == 0) || size == L) == ((k & stride) == 0);
-                    sa = keep_min ? rmin(sa, oa) : rmax(sa, oa);
-                    sb = keep_min ? rmin(sb, ob) : rmax(sb, ob);
+                    for (int d = size >> 2; d > 0; d >>= 1) {
+                        const bool lowd = (k & d) == 0;
+                        const real px = __shfl_xor_sync(0xffffffffu, x, d);
+                        const real py = __shfl_xor_sync(0xffffffffu, y, d);
+                        x = lowd ? rmin(x, px) : rmax(x, px);
+                        y = lowd ? rmin(y, py) : rmax(y, py);
+                    }
+                    const real mn = rmin(x, y);
+                    y = rmax(x, y);
+                    x = mn;
                 }
             }
-            const real rb = __shfl_sync(0xffffffffu, sb, (L - 1 - k), L);
-            real lo = rmin(sa, rb), hi = rmax(sa, rb);
+            const bool lowh = (k & (L >> 1)) == 0;
+            real v = lowh ? rmax(x, y) : rmin(x, y);
 #pragma unroll
-            for (int d = 1; d < L; d <<= 1) {
-                lo = rmax(lo, __shfl_xor_sync(0xffffffffu, lo, d));
-                hi = rmin(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+            for (int d = 1; d < (L >> 1); d <<= 1) {
+                const real pv = __shfl_xor_sync(0xffffffffu, v, d);
+                v = lowh ? rmax(v, pv) : rmin(v, pv);
             }
+            const real w = __shfl_xor_sync(0xffffffffu, v, L >> 1);
+            const real lo = lowh ? v : w, hi = lowh ? w : v;
             bool k0, k1;  // candidate survives
             if (__all_sync(0xffffffffu, lo < hi)) {  // no tie across the list boundary in any frame of the warp (lo finite)
                 k0 = c0 < hi;
@@ -305,16 +339,24 @@ __global__ void __launch_bounds__(32) list_decode_kernel(const ListArgs a)
             const uint32_t fmask = LMASK << fbase;
             const uint32_t both = m0 & m1 & fmask, dead = ~(m0 | m1) & fmask;
             int src = lane;
-            if (!(k0 || k1)) {
-                // t-th free slot (ascending) takes the bit-1 branch of the t-th both-survivor (ascending): SCL_1024.c:636-660
-                const int td = __popc(dead & ((1u << lane) - 1u));
-                if (td < __popc(both)) src = (int)__fns(both, 0, td + 1);
+            if (__any_sync(0xffffffffu, !(k0 || k1))) {
+                // t-th free slot (ascending) takes the bit-1 branch of the t-th both-survivor (ascending): SCL_1024.c:636-660.
+                // The both-survivors publish their lane at their rank; the free slots read the entry of their own rank.
+                const uint32_t below = (1u << lane) - 1u;
+                if (k0 && k1) sm_slot[fbase + __popc(both & below)] = (uint32_t)lane;
+                __syncwarp();
+                if (!(k0 || k1) && __popc(dead & below) < __popc(both)) src = (int)sm_slot[fbase + __popc(dead & below)];
+                __syncwarp();
             }
             const real pc1 = __shfl_sync(0xffffffffu, c1, src);
+            if (keep2) {  // stage 2 is read again by the g step before leaf 2 only
 #pragma unroll
-            for (int e = 0; e < 4; e++) s2[e] = __shfl_sync(0xffffffffu, s2[e], src);
-            s1[0] = __shfl_sync(0xffffffffu, s1[0], src);
-            s1[1] = __shfl_sync(0xffffffffu, s1[1], src);
+                for (int e = 0; e < 4; e++) s2[e] = __shfl_sync(0xffffffffu, s2[e], src);
+            }
+            if (first) {  // stage 1 is read by the g step of the odd leaf that follows
+                s1[0] = __shfl_sync(0xffffffffu, s1[0], src);
+                s1[1] = __shfl_sync(0xffffffffu, s1[1], src);
+            }
             ptr = __shfl_sync(0xffffffffu, ptr, src);
             bptr = __shfl_sync(0xffffffffu, bptr, src);
             Blow = __shfl_sync(0xffffffffu, Blow, src);
@@ -329,40 +371,64 @@ __global__ void __launch_bounds__(32) list_decode_kernel(const ListArgs a)
         };
 
         // =================================================================== the N/4 leaf groups
+        V4 *const st3 = stage_at(3), *const st4 = stage_at(4);
 #pragma unroll 1
         for (int j4 = 0; j4 < N / 4; j4++) {
-            const bool coop = (L > 1) && (j4 < a.coop_groups);
-            int s = LOGN - 1;
-            if (j4 != 0) {
-                s = __ffs(j4) - 1 + 2;
-                g_layer(s, coop);
-                s--;
-            }
-#pragma unroll 1
-            for (; s >= 2; s--) f_layer(s, coop);
-            ug = 0;
-            {   // stage 2 of this 4-block (home array, or slot 0's while the lanes cooperate); kept in registers, cloned by shuffle
-                const V4 v = ldv(stage_at(2) + fbase + pfield(2));
+            // ---- descend to stage 2 of this 4-block.  Stage 2 lives in registers only (its four values are consumed by
+            // the four leaves below and cloned by shuffle); stage 3 goes through registers to the f step that follows it.
+            if (j4 & 1) {  // g at stage 2 from stage 3 (via the pointer word)
+                const V4 *src = st3 + fbase + pfield(3);
+                const V4 v = g4<real>(ldv(src), ldv(src + 32), Blow & 0xFu);
 #pragma unroll
                 for (int e = 0; e < 4; e++) s2[e] = v.v[e];
-            }
-#pragma unroll 1
-            for (int i = 0; i < 4; i++) {
-                real lam;
-                if (!(i & 1)) {
-                    if (i == 0) {  // f at stage 1
-                        s1[0] = chk_lean<real>(s2[0], s2[2]);
-                        s1[1] = chk_lean<real>(s2[1], s2[3]);
-                    } else {       // g at stage 1, partial sums (u0^u1, u1)
-                        s1[0] = s2[2] + RT::flip(s2[0], (ug ^ (ug >> 1)) & 1u);
-                        s1[1] = s2[3] + RT::flip(s2[1], (ug >> 1) & 1u);
+            } else {
+                V4 a3, b3;
+                int top = 3;
+                if (j4 & 2) {  // g at stage 3 from stage 4 (via the pointer word)
+                    const V4 *src = st4 + fbase + pfield(4);
+                    const uint32_t bw = Blow >> 4;
+                    a3 = g4<real>(ldv(src), ldv(src + 64), bw & 0xFu);
+                    b3 = g4<real>(ldv(src + 32), ldv(src + 96), (bw >> 4) & 0xFu);
+                } else {       // a longer chain: g at the stage the finished block opens, f-layers down to stage 4, f at stage 3
+                    const bool coop = (L > 1) && (j4 < a.coop_groups);
+                    int s = LOGN - 1;
+                    if (j4 != 0) {
+                        s = __ffs(j4) - 1 + 2;
+                        if (!coop) top = s;
+                        g_layer(s, coop);
+                        s--;
+                    } else if (!coop) {
+                        top = s;
                     }
-                    lam = chk_lean<real>(s1[0], s1[1]);                              // f at stage 0
-                } else {
-                    lam = s1[1] + RT::flip(s1[0], (ug >> (i - 1)) & 1u);        // g at stage 0
+#pragma unroll 1
+                    for (; s >= 4; s--) f_layer(s, coop);
+                    const V4 *src = st4 + (coop ? fbase : lane);  // own home, or slot 0's while the frame's lanes cooperate
+                    a3 = f4<real>(ldv(src), ldv(src + 64));
+                    b3 = f4<real>(ldv(src + 32), ldv(src + 96));
                 }
-                const uint32_t u = leaf(4 * j4 + i, lam);
-                ug |= u << i;
+                stv(st3 + lane, a3);
+                stv(st3 + 32 + lane, b3);
+                const V4 v = f4<real>(a3, b3);
+#pragma unroll
+                for (int e = 0; e < 4; e++) s2[e] = v.v[e];
+                set_pfields(top);
+                __syncwarp();
+            }
+            ug = 0;
+            const uint32_t inib = a.m.info[j4 >> 3] >> ((j4 & 7) * 4);  // which of the four leaves carry information
+#pragma unroll 1
+            for (int p = 0; p < 2; p++) {
+                if (p == 0) {  // f at stage 1
+                    s1[0] = chk_lean<real>(s2[0], s2[2]);
+                    s1[1] = chk_lean<real>(s2[1], s2[3]);
+                } else {       // g at stage 1, partial sums (u0^u1, u1)
+                    s1[0] = s2[2] + RT::flip(s2[0], (ug ^ (ug >> 1)) & 1u);
+                    s1[1] = s2[3] + RT::flip(s2[1], (ug >> 1) & 1u);
+                }
+                const uint32_t ua = leaf((inib >> (2 * p)) & 1u, chk_lean<real>(s1[0], s1[1]), true, p == 0);   // f at stage 0
+                ug |= ua << (2 * p);  // ug travels with the path when the next leaf clones it
+                const uint32_t ub = leaf((inib >> (2 * p + 1)) & 1u, s1[1] + RT::flip(s1[0], ua), false, p == 0);  // g at stage 0
+                ug |= ub << (2 * p + 1);
             }
 
             // ---- partial sums of the finished 4-block, pushed up while the block closes larger blocks -------
@@ -508,6 +574,9 @@ struct ListDispatch {
     }
 };
 
+#ifdef POLAR_DEV_CASES  // development builds: only the bench / parity configurations (compile time)
+#define POLAR_LIST_CASES(X) X(7, 8) X(10, 1) X(10, 8)
+#else
 #define POLAR_LIST_CASES(X) \
     X(5, 1) X(5, 2) X(5, 4) X(5, 8) \
     X(6, 1) X(6, 2) X(6, 4) X(6, 8) \
@@ -515,6 +584,7 @@ struct ListDispatch {
     X(8, 1) X(8, 2) X(8, 4) X(8, 8) X(8, 16) X(8, 32) \
     X(9, 1) X(9, 2) X(9, 4) X(9, 8) X(9, 16) X(9, 32) \
     X(10, 1) X(10, 2) X(10, 4) X(10, 8) X(10, 16) X(10, 32)
+#endif
 
 cudaError_t list_plan(int n, int L, bool f64, ListPlan *plan)
 {
