@@ -53,6 +53,8 @@ int ilog2(int v) { int k = 0; while ((1 << k) < v) k++; return k; }
 
 }  // namespace
 
+constexpr int kPipeBufs = 4;
+
 struct pg_ctx {
     pg_params p;
     int n = 0, W = 0, nI = 0;
@@ -85,13 +87,15 @@ struct pg_ctx {
     unsigned long long *h_counters = nullptr;  // pinned, CNT_N
     void *d_scratch = nullptr;
     int grid = 0;
-    // second buffer set + copy stream for the pipelined host path (pg_decode_llr*: H2D of chunk i+1 overlaps decode of chunk i)
-    cudaStream_t st_copy = nullptr;
-    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    size_t scratch_per_cta = 0;
+    // pipelined host path (pg_decode_llr*): a copy stream feeds kPipeBufs buffer sets; the list decoders run two half-grid
+    // kernels side by side on two compute streams (their phases interleave instead of marching in lockstep), BP runs one
+    cudaStream_t st_copy = nullptr, st2 = nullptr;
+    cudaEvent_t ev_h2d[kPipeBufs] = {}, ev_free[kPipeBufs] = {};
     size_t pipe_cap = 0;
-    void *p_llr[2] = {nullptr, nullptr}, *p_in[2] = {nullptr, nullptr};
-    uint32_t *p_uhat[2] = {nullptr, nullptr}, *p_info[2] = {nullptr, nullptr};
-    uint8_t *p_bytes[2] = {nullptr, nullptr};
+    void *p_llr[kPipeBufs] = {}, *p_in[kPipeBufs] = {};
+    uint32_t *p_uhat[kPipeBufs] = {}, *p_info[kPipeBufs] = {};
+    uint8_t *p_bytes[kPipeBufs] = {};
     size_t chunk_max = 0;
 
     ncclComm_t comm = nullptr;
@@ -168,14 +172,15 @@ static int ensure_pipe(pg_ctx *ctx, size_t frames, bool want_bytes)
 {
     if (!ctx->st_copy) {
         CU(cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking));
-        for (int s = 0; s < 2; s++) {
+        CU(cudaStreamCreateWithFlags(&ctx->st2, cudaStreamNonBlocking));
+        for (int s = 0; s < kPipeBufs; s++) {
             CU(cudaEventCreateWithFlags(&ctx->ev_h2d[s], cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&ctx->ev_free[s], cudaEventDisableTiming));
         }
     }
     if (frames <= ctx->pipe_cap && (!want_bytes || ctx->p_bytes[0])) return PG_OK;
     const size_t N = ctx->p.N, W = ctx->W;
-    for (int s = 0; s < 2; s++) {
+    for (int s = 0; s < kPipeBufs; s++) {
         cudaFree(ctx->p_llr[s]); cudaFree(ctx->p_in[s]); cudaFree(ctx->p_uhat[s]); cudaFree(ctx->p_info[s]); cudaFree(ctx->p_bytes[s]);
         ctx->p_llr[s] = ctx->p_in[s] = nullptr; ctx->p_uhat[s] = ctx->p_info[s] = nullptr; ctx->p_bytes[s] = nullptr;
         CU(cudaMalloc(&ctx->p_llr[s], frames * N * (ctx->f64 ? 8 : 4)));
@@ -297,6 +302,7 @@ extern "C" int pg_create(const pg_params *p, pg_ctx **out)
         int per_sm = lp.ctas_per_sm;
         if (const char *cap = getenv("POLARGPU_LIST_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(cap)));  // tuning aid
         ctx->grid = ctx->sm_count * per_sm;
+        ctx->scratch_per_cta = lp.scratch_per_cta;
         if (lp.scratch_per_cta) CUC(cudaMalloc(&ctx->d_scratch, lp.scratch_per_cta * (size_t)ctx->grid));
     }
     {
@@ -319,12 +325,14 @@ extern "C" void pg_destroy(pg_ctx *ctx)
     if (ctx->st) cudaStreamSynchronize(ctx->st);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     free_buffers(ctx);
-    for (int s = 0; s < 2; s++) {
+    if (ctx->st2) cudaStreamSynchronize(ctx->st2);
+    for (int s = 0; s < kPipeBufs; s++) {
         cudaFree(ctx->p_llr[s]); cudaFree(ctx->p_in[s]); cudaFree(ctx->p_uhat[s]); cudaFree(ctx->p_info[s]); cudaFree(ctx->p_bytes[s]);
         if (ctx->ev_h2d[s]) cudaEventDestroy(ctx->ev_h2d[s]);
         if (ctx->ev_free[s]) cudaEventDestroy(ctx->ev_free[s]);
     }
     if (ctx->st_copy) cudaStreamDestroy(ctx->st_copy);
+    if (ctx->st2) cudaStreamDestroy(ctx->st2);
     cudaFree(ctx->d_I); cudaFree(ctx->d_crc_masks); cudaFree(ctx->d_crc_sys); cudaFree(ctx->d_counters); cudaFree(ctx->d_queue);
     cudaFree(ctx->d_bpr); cudaFree(ctx->d_scratch); cudaFree(ctx->d_xchg);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
@@ -383,10 +391,13 @@ static int run_channel(pg_ctx *ctx, double ebn0_db, uint64_t first, size_t B, bo
     return run_channel_to(ctx, ebn0_db, first, B, want_llr ? ctx->d_llr : nullptr, ctx->d_truth);
 }
 
-static int run_decode(pg_ctx *ctx, const void *d_llr, size_t B, const uint32_t *d_truth, uint32_t *d_uhat, uint32_t *d_info, bool count)
+// decode B frames on stream `st` with at most `grid_cap` CTAs that use the scratch slots [cta_off, cta_off + grid_cap)
+static int run_decode_on(pg_ctx *ctx, cudaStream_t st, int grid_cap, int cta_off, const void *d_llr, size_t B, const uint32_t *d_truth,
+                         uint32_t *d_uhat, uint32_t *d_info, bool count)
 {
     const pg_params &p = ctx->p;
-    CU(cudaEventRecord(ctx->ev[2], ctx->st));
+    const bool timed = (st == ctx->st);
+    if (timed) CU(cudaEventRecord(ctx->ev[2], st));
     if (p.decoder == PG_DEC_BP) {
         BpArgs a;
         std::memset(&a, 0, sizeof(a));
@@ -398,21 +409,21 @@ static int run_decode(pg_ctx *ctx, const void *d_llr, size_t B, const uint32_t *
         std::memcpy(a.bpr_samples, ctx->bpr_samples, sizeof(a.bpr_samples));
         a.B = B; a.iters = p.iter_max; a.early_stop = p.bp_early_stop;
         a.m = ctx->masks;
-        CU(cudaMemsetAsync(ctx->d_queue, 0, 8, ctx->st));
+        CU(cudaMemsetAsync(ctx->d_queue, 0, 8, st));
         if (ctx->h2) {
             if (a.bpr_E) { ctx->err = "the BPR statistic is not available in PG_REAL_H2 mode"; return PG_ERR_UNSUPPORTED; }
-            const int grid = (int)std::min<size_t>((size_t)ctx->grid, (B + 1) / 2);
-            CU(launch_bp_h2(a, ctx->n, std::max(grid, 1), ctx->st));
+            const int grid = (int)std::min<size_t>((size_t)grid_cap, (B + 1) / 2);
+            CU(launch_bp_h2(a, ctx->n, std::max(grid, 1), st));
         } else {
-            const int grid = (int)std::min<size_t>((size_t)ctx->grid, B);
-            CU(launch_bp(a, ctx->n, ctx->f64, std::max(grid, 1), ctx->st));
+            const int grid = (int)std::min<size_t>((size_t)grid_cap, B);
+            CU(launch_bp(a, ctx->n, ctx->f64, std::max(grid, 1), st));
         }
     } else {
         ListArgs a;
         std::memset(&a, 0, sizeof(a));
         a.llr = d_llr; a.truth = d_truth; a.u_hat = d_uhat; a.frame_info = d_info;
         a.counters = count ? ctx->d_counters : nullptr;
-        a.gscratch = ctx->d_scratch;
+        a.gscratch = ctx->d_scratch ? (char *)ctx->d_scratch + (size_t)cta_off * ctx->scratch_per_cta : nullptr;
         a.crc_masks = ctx->d_crc_masks;
         a.B = B; a.r = p.crc_bits; a.use_crc = (p.decoder == PG_DEC_CASCL);
         {
@@ -423,13 +434,20 @@ static int run_decode(pg_ctx *ctx, const void *d_llr, size_t B, const uint32_t *
         a.m = ctx->masks;
         const size_t fpw = 32 / (size_t)p.list_size;
         const size_t groups = (B + fpw - 1) / fpw;
-        const int grid = (int)std::min<size_t>((size_t)ctx->grid, groups);
-        CU(launch_list(a, ctx->n, p.list_size, ctx->f64, std::max(grid, 1), ctx->st));
+        const int grid = (int)std::min<size_t>((size_t)grid_cap, groups);
+        CU(launch_list(a, ctx->n, p.list_size, ctx->f64, std::max(grid, 1), st));
     }
-    CU(cudaEventRecord(ctx->ev[3], ctx->st));
-    ctx->ev_dec = true;
+    if (timed) {
+        CU(cudaEventRecord(ctx->ev[3], st));
+        ctx->ev_dec = true;
+    }
     ctx->launches++;
     return debug_sync(ctx, "decode");
+}
+
+static int run_decode(pg_ctx *ctx, const void *d_llr, size_t B, const uint32_t *d_truth, uint32_t *d_uhat, uint32_t *d_info, bool count)
+{
+    return run_decode_on(ctx, ctx->st, ctx->grid, 0, d_llr, B, d_truth, d_uhat, d_info, count);
 }
 
 extern "C" int pg_decode_llr_device(pg_ctx *ctx, const void *d_llr, int llr_is_f64, size_t B, uint32_t *d_u_hat_packed, uint32_t *d_flags)
@@ -492,32 +510,39 @@ static int decode_host(pg_ctx *ctx, const void *llr, int llr_is_f64, size_t B, u
     const size_t N = ctx->p.N, W = ctx->W;
     const size_t esz = llr_is_f64 ? 8 : 4;
     const bool conv = (llr_is_f64 != 0) != ctx->f64;
-    const size_t pc = std::min<size_t>(ctx->chunk_max, std::max<size_t>((size_t)wave_frames(ctx), 1024));
+    // Chunk = what one launch keeps resident.  A wave-sized launch runs all its warps in lockstep through the same phases of the
+    // schedule (memory-heavy top layers, then leaf-heavy stretches), which costs the list kernel ~15 %; two half-grid launches on
+    // two streams, offset by half a chunk, interleave those phases and halve the pipeline fill.
+    const int lanes = (ctx->p.decoder != PG_DEC_BP && ctx->grid >= 2 && !getenv("POLARGPU_ONE_LANE")) ? 2 : 1;
+    const int nbuf = 2 * lanes, lane_grid = ctx->grid / lanes;
+    const size_t pc = std::min<size_t>(ctx->chunk_max, std::max<size_t>((size_t)wave_frames(ctx) / lanes, 1024));
     if (B > pc && !getenv("POLARGPU_NO_PIPELINE")) {
         int rc = ensure_pipe(ctx, pc, u_hat != nullptr);
         if (rc) return rc;
         size_t i = 0;
         for (size_t off = 0; off < B; off += pc, i++) {
             const size_t b = std::min(pc, B - off);
-            const int s = (int)(i & 1);
-            if (i >= 2) CU(cudaStreamWaitEvent(ctx->st_copy, ctx->ev_free[s], 0));
+            const int s = (int)(i % nbuf), lane = (int)(i % lanes);
+            cudaStream_t cs = lane ? ctx->st2 : ctx->st;
+            if (i >= (size_t)nbuf) CU(cudaStreamWaitEvent(ctx->st_copy, ctx->ev_free[s], 0));
             void *dst = conv ? ctx->p_in[s] : ctx->p_llr[s];
             CU(cudaMemcpyAsync(dst, (const char *)llr + off * N * esz, b * N * esz, cudaMemcpyHostToDevice, ctx->st_copy));
             CU(cudaEventRecord(ctx->ev_h2d[s], ctx->st_copy));
-            CU(cudaStreamWaitEvent(ctx->st, ctx->ev_h2d[s], 0));
-            if (conv) { CU(launch_convert_llr(ctx->p_in[s], llr_is_f64 != 0, ctx->p_llr[s], ctx->f64, b * N, ctx->st)); ctx->launches++; }
-            rc = run_decode(ctx, ctx->p_llr[s], b, nullptr, ctx->p_uhat[s], ctx->p_info[s], false);
+            CU(cudaStreamWaitEvent(cs, ctx->ev_h2d[s], 0));
+            if (conv) { CU(launch_convert_llr(ctx->p_in[s], llr_is_f64 != 0, ctx->p_llr[s], ctx->f64, b * N, cs)); ctx->launches++; }
+            rc = run_decode_on(ctx, cs, lane_grid, lane * lane_grid, ctx->p_llr[s], b, nullptr, ctx->p_uhat[s], ctx->p_info[s], false);
             if (rc) return rc;
             if (u_hat) {
-                CU(launch_unpack_bits(ctx->p_uhat[s], ctx->p_bytes[s], b, (int)N, ctx->st));
+                CU(launch_unpack_bits(ctx->p_uhat[s], ctx->p_bytes[s], b, (int)N, cs));
                 ctx->launches++;
-                CU(cudaMemcpyAsync(u_hat + off * N, ctx->p_bytes[s], b * N, cudaMemcpyDeviceToHost, ctx->st));
+                CU(cudaMemcpyAsync(u_hat + off * N, ctx->p_bytes[s], b * N, cudaMemcpyDeviceToHost, cs));
             }
-            if (u_hat_packed) CU(cudaMemcpyAsync(u_hat_packed + off * W, ctx->p_uhat[s], b * W * 4, cudaMemcpyDeviceToHost, ctx->st));
-            if (flags) CU(cudaMemcpyAsync(flags + off, ctx->p_info[s], b * 4, cudaMemcpyDeviceToHost, ctx->st));
-            CU(cudaEventRecord(ctx->ev_free[s], ctx->st));
+            if (u_hat_packed) CU(cudaMemcpyAsync(u_hat_packed + off * W, ctx->p_uhat[s], b * W * 4, cudaMemcpyDeviceToHost, cs));
+            if (flags) CU(cudaMemcpyAsync(flags + off, ctx->p_info[s], b * 4, cudaMemcpyDeviceToHost, cs));
+            CU(cudaEventRecord(ctx->ev_free[s], cs));
         }
         CU(cudaStreamSynchronize(ctx->st));
+        if (lanes > 1) CU(cudaStreamSynchronize(ctx->st2));
     } else {
         for (size_t off = 0; off < B; off += ctx->chunk_max) {
             const size_t b = std::min(ctx->chunk_max, B - off);

@@ -129,7 +129,7 @@ __device__ __forceinline__ vec4<real> g4(const vec4<real> &up, const vec4<real> 
 }
 
 template <typename real, int LOGN, int L, int SMEM_TOP, int BITS_TOP>
-__global__ void __launch_bounds__(32, (sizeof(real) == 4) ? 32 : 16) list_decode_kernel(const ListArgs a)
+__global__ void __launch_bounds__(32, (sizeof(real) == 4) ? 32 : 24) list_decode_kernel(const ListArgs a)
 {
     using C = ListCfg<real, LOGN, L, SMEM_TOP, BITS_TOP>;
     using RT = real_traits<real>;
