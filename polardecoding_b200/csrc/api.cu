@@ -53,7 +53,7 @@ int ilog2(int v) { int k = 0; while ((1 << k) < v) k++; return k; }
 
 }  // namespace
 
-constexpr int kPipeBufs = 4;
+constexpr int kPipeLanes = 4, kPipeBufs = 2 * kPipeLanes;
 
 struct pg_ctx {
     pg_params p;
@@ -88,9 +88,10 @@ struct pg_ctx {
     void *d_scratch = nullptr;
     int grid = 0;
     size_t scratch_per_cta = 0;
-    // pipelined host path (pg_decode_llr*): a copy stream feeds kPipeBufs buffer sets; the list decoders run two half-grid
-    // kernels side by side on two compute streams (their phases interleave instead of marching in lockstep), BP runs one
-    cudaStream_t st_copy = nullptr, st2 = nullptr;
+    // pipelined host path (pg_decode_llr*): a copy stream feeds two buffer sets per lane; the list decoders run kPipeLanes
+    // quarter-grid kernels side by side on as many compute streams (their phases interleave instead of marching in lockstep),
+    // BP runs one
+    cudaStream_t st_copy = nullptr, st_lane[kPipeLanes] = {};  // st_lane[0] is st
     cudaEvent_t ev_h2d[kPipeBufs] = {}, ev_free[kPipeBufs] = {};
     size_t pipe_cap = 0;
     void *p_llr[kPipeBufs] = {}, *p_in[kPipeBufs] = {};
@@ -172,7 +173,8 @@ static int ensure_pipe(pg_ctx *ctx, size_t frames, bool want_bytes)
 {
     if (!ctx->st_copy) {
         CU(cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking));
-        CU(cudaStreamCreateWithFlags(&ctx->st2, cudaStreamNonBlocking));
+        ctx->st_lane[0] = ctx->st;
+        for (int l = 1; l < kPipeLanes; l++) CU(cudaStreamCreateWithFlags(&ctx->st_lane[l], cudaStreamNonBlocking));
         for (int s = 0; s < kPipeBufs; s++) {
             CU(cudaEventCreateWithFlags(&ctx->ev_h2d[s], cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&ctx->ev_free[s], cudaEventDisableTiming));
@@ -325,14 +327,16 @@ extern "C" void pg_destroy(pg_ctx *ctx)
     if (ctx->st) cudaStreamSynchronize(ctx->st);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     free_buffers(ctx);
-    if (ctx->st2) cudaStreamSynchronize(ctx->st2);
+    for (int l = 1; l < kPipeLanes; l++)
+        if (ctx->st_lane[l]) cudaStreamSynchronize(ctx->st_lane[l]);
     for (int s = 0; s < kPipeBufs; s++) {
         cudaFree(ctx->p_llr[s]); cudaFree(ctx->p_in[s]); cudaFree(ctx->p_uhat[s]); cudaFree(ctx->p_info[s]); cudaFree(ctx->p_bytes[s]);
         if (ctx->ev_h2d[s]) cudaEventDestroy(ctx->ev_h2d[s]);
         if (ctx->ev_free[s]) cudaEventDestroy(ctx->ev_free[s]);
     }
     if (ctx->st_copy) cudaStreamDestroy(ctx->st_copy);
-    if (ctx->st2) cudaStreamDestroy(ctx->st2);
+    for (int l = 1; l < kPipeLanes; l++)
+        if (ctx->st_lane[l]) cudaStreamDestroy(ctx->st_lane[l]);
     cudaFree(ctx->d_I); cudaFree(ctx->d_crc_masks); cudaFree(ctx->d_crc_sys); cudaFree(ctx->d_counters); cudaFree(ctx->d_queue);
     cudaFree(ctx->d_bpr); cudaFree(ctx->d_scratch); cudaFree(ctx->d_xchg);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
@@ -511,9 +515,12 @@ static int decode_host(pg_ctx *ctx, const void *llr, int llr_is_f64, size_t B, u
     const size_t esz = llr_is_f64 ? 8 : 4;
     const bool conv = (llr_is_f64 != 0) != ctx->f64;
     // Chunk = what one launch keeps resident.  A wave-sized launch runs all its warps in lockstep through the same phases of the
-    // schedule (memory-heavy top layers, then leaf-heavy stretches), which costs the list kernel ~15 %; two half-grid launches on
-    // two streams, offset by half a chunk, interleave those phases and halve the pipeline fill.
-    const int lanes = (ctx->p.decoder != PG_DEC_BP && ctx->grid >= 2 && !getenv("POLARGPU_ONE_LANE")) ? 2 : 1;
+    // schedule (memory-heavy top layers, then leaf-heavy stretches), which costs the list kernel ~15 %; four quarter-grid launches on
+    // four streams, offset by a quarter chunk each, interleave those phases and quarter the pipeline fill
+    // (measured, 8 waves of CA-SCL 1024: 10.0 / 11.35 / 11.8 Mframes/s with 1 / 2 / 4 lanes).
+    int lanes = (ctx->p.decoder != PG_DEC_BP) ? kPipeLanes : 1;
+    if (const char *e = getenv("POLARGPU_LANES")) lanes = std::max(1, std::min(kPipeLanes, atoi(e)));  // tuning aid
+    if (ctx->p.decoder == PG_DEC_BP || ctx->grid < lanes) lanes = 1;
     const int nbuf = 2 * lanes, lane_grid = ctx->grid / lanes;
     const size_t pc = std::min<size_t>(ctx->chunk_max, std::max<size_t>((size_t)wave_frames(ctx) / lanes, 1024));
     if (B > pc && !getenv("POLARGPU_NO_PIPELINE")) {
@@ -523,7 +530,7 @@ static int decode_host(pg_ctx *ctx, const void *llr, int llr_is_f64, size_t B, u
         for (size_t off = 0; off < B; off += pc, i++) {
             const size_t b = std::min(pc, B - off);
             const int s = (int)(i % nbuf), lane = (int)(i % lanes);
-            cudaStream_t cs = lane ? ctx->st2 : ctx->st;
+            cudaStream_t cs = ctx->st_lane[lane];
             if (i >= (size_t)nbuf) CU(cudaStreamWaitEvent(ctx->st_copy, ctx->ev_free[s], 0));
             void *dst = conv ? ctx->p_in[s] : ctx->p_llr[s];
             CU(cudaMemcpyAsync(dst, (const char *)llr + off * N * esz, b * N * esz, cudaMemcpyHostToDevice, ctx->st_copy));
@@ -541,8 +548,7 @@ static int decode_host(pg_ctx *ctx, const void *llr, int llr_is_f64, size_t B, u
             if (flags) CU(cudaMemcpyAsync(flags + off, ctx->p_info[s], b * 4, cudaMemcpyDeviceToHost, cs));
             CU(cudaEventRecord(ctx->ev_free[s], cs));
         }
-        CU(cudaStreamSynchronize(ctx->st));
-        if (lanes > 1) CU(cudaStreamSynchronize(ctx->st2));
+        for (int l = 0; l < lanes; l++) CU(cudaStreamSynchronize(ctx->st_lane[l]));
     } else {
         for (size_t off = 0; off < B; off += ctx->chunk_max) {
             const size_t b = std::min(ctx->chunk_max, B - off);
