@@ -227,18 +227,8 @@ __global__ void __launch_bounds__(32, (sizeof(real) == 4) ? 32 : 24) list_decode
         };
 
         // ---- g-layer producing stage t (4 <= t < LOGN) from stage t+1 (via the pointer word) and the partial sums B[t]
-        auto g_layer = [&](int t, bool coop) {
+        auto g_layer = [&](int t) {
             const int cnt4 = 1 << (t - 2);
-            if (coop) {  // as above; the partial sums of an all-frozen prefix are zero, so g = lower + upper
-                V4 *dst = stage_at(t) + fbase;
-                const V4 *src = ch4;
-                int stride = 1;
-                if (t + 1 != LOGN) { src = stage_at(t + 1) + fbase; stride = 32; }
-#pragma unroll 1
-                for (int i4 = k; i4 < cnt4; i4 += L) stv(dst + i4 * 32, g4<real>(ldv(src + i4 * stride), ldv(src + (i4 + cnt4) * stride), 0u));
-                __syncwarp();
-                return;
-            }
             V4 *dst = stage_at(t) + lane;
             const V4 *src = ch4;
             int stride = 1;
@@ -372,8 +362,84 @@ __global__ void __launch_bounds__(32, (sizeof(real) == 4) ? 32 : 24) list_decode
 
         // =================================================================== the N/4 leaf groups
         V4 *const st3 = stage_at(3), *const st4 = stage_at(4);
+
+        // =================================================================== the frozen prefix
+        // Before the first information bit a frame has ONE path and every decision is 0, so the schedule has no data dependence:
+        // the subtree over the first 2^D leaves (D = bits of the first information index) is a plain butterfly with g = lower +
+        // upper.  The frame's L lanes split it: f-layers down to stage D, then in-place levels D-1..2 in slot 0's stage-D array,
+        // then the two in-register levels and PHI per leaf.  The path metric is the sum of the leaf penalties IN LEAF ORDER
+        // (bit-exact with the reference's running sum), taken by every lane from the stored penalties.  On the way down the
+        // block that holds the first information bit is copied into slot 0's arrays of every stage, which is the state the
+        // loop below resumes from (all pointer fields 0, all partial sums 0).
+        int j4_start = 0;
+        if (L > 1 && a.coop_groups >= 2) {
+            int P = a.coop_groups;
+            if (P > N / 8) P = N / 8;               // keep the subtree inside the first half: its root is then an f-layer output
+            const int D = 32 - __clz(4 * P - 1);    // smallest subtree [0, 2^D) that holds the leaves 0..4P-1; 3 <= D <= LOGN-1
+            const bool inside = 4 * P < (1 << D);   // it also holds leaf 4P: the loop resumes inside it
+            for (int s = LOGN - 1; s >= D; s--) f_layer(s, true);
+            V4 *const buf = stage_at(D) + fbase;  // V4 i of the subtree at buf[i * 32]
+            const int n4 = 1 << (D - 2);
 #pragma unroll 1
-        for (int j4 = 0; j4 < N / 4; j4++) {
+            for (int s = D - 1; s >= 2; s--) {    // level s: blocks of 2^(s+1) values -> f half | g half
+                const int h4 = 1 << (s - 2);      // V4s per half
+#pragma unroll 1
+                for (int q = k; q < (n4 >> 1); q += L) {
+                    const int i4 = ((q >> (s - 2)) << (s - 1)) | (q & (h4 - 1));
+                    const V4 up = ldv(buf + i4 * 32), lo = ldv(buf + (i4 + h4) * 32);
+                    stv(buf + i4 * 32, f4<real>(up, lo));
+                    stv(buf + (i4 + h4) * 32, g4<real>(up, lo, 0u));
+                }
+                __syncwarp();
+                if (inside && s >= 3) {  // the stage-s block that contains leaf 4P
+                    V4 *dst = stage_at(s) + fbase;
+                    const int b4 = ((4 * P) >> s) << (s - 2);
+#pragma unroll 1
+                    for (int q = k; q < h4; q += L) stv(dst + q * 32, ldv(buf + (b4 + q) * 32));
+                    __syncwarp();
+                }
+            }
+#pragma unroll 1
+            for (int q = k; q < n4; q += L) {     // levels 1 and 0 of one 4-block, then the penalties of its four leaves
+                const V4 v = ldv(buf + q * 32);
+                const real f0 = chk_lean<real>(v.v[0], v.v[2]), f1 = chk_lean<real>(v.v[1], v.v[3]);
+                const real g0 = v.v[2] + v.v[0], g1 = v.v[3] + v.v[1];
+                real lam[4] = {chk_lean<real>(f0, f1), f1 + f0, chk_lean<real>(g0, g1), g1 + g0};
+                V4 pen;
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const real ab = rabs(lam[e]);
+                    const real t = tbl8<real>(ab);
+                    real tp = t;
+                    tp += ab;                      // PHI of a frozen leaf: table, plus |l| when l < 0 (SCL_1024.c:489-500)
+                    pen.v[e] = (lam[e] < (real)0) ? tp : t;
+                }
+                stv(buf + q * 32, pen);
+            }
+            __syncwarp();
+            real acc = (real)0;
+#pragma unroll 1
+            for (int q = 0; q < P; q++) {
+                const V4 pen = ldv(buf + q * 32);
+                acc = acc + pen.v[0];
+                acc = acc + pen.v[1];
+                acc = acc + pen.v[2];
+                acc = acc + pen.v[3];
+            }
+            if (k == 0) pm = acc;
+            // partial sums of the prefix are zero: slot 0's bit arrays (every pointer field says slot 0)
+#pragma unroll 1
+            for (int sb = 6; sb <= LOGN; sb++) {
+                uint32_t *z = bits_at(sb) + fbase;
+#pragma unroll 1
+                for (int w = k; w < (1 << (sb - 5)); w += L) z[w * 32] = 0u;
+            }
+            __syncwarp();
+            j4_start = P;
+        }
+
+#pragma unroll 1
+        for (int j4 = j4_start; j4 < N / 4; j4++) {
             // ---- descend to stage 2 of this 4-block.  Stage 2 lives in registers only (its four values are consumed by
             // the four leaves below and cloned by shuffle); stage 3 goes through registers to the f step that follows it.
             if (j4 & 1) {  // g at stage 2 from stage 3 (via the pointer word)
@@ -390,19 +456,17 @@ __global__ void __launch_bounds__(32, (sizeof(real) == 4) ? 32 : 24) list_decode
                     a3 = g4<real>(ldv(src), ldv(src + 64), bw & 0xFu);
                     b3 = g4<real>(ldv(src + 32), ldv(src + 96), (bw >> 4) & 0xFu);
                 } else {       // a longer chain: g at the stage the finished block opens, f-layers down to stage 4, f at stage 3
-                    const bool coop = (L > 1) && (j4 < a.coop_groups);
                     int s = LOGN - 1;
+                    top = s;
                     if (j4 != 0) {
                         s = __ffs(j4) - 1 + 2;
-                        if (!coop) top = s;
-                        g_layer(s, coop);
-                        s--;
-                    } else if (!coop) {
                         top = s;
+                        g_layer(s);
+                        s--;
                     }
 #pragma unroll 1
-                    for (; s >= 4; s--) f_layer(s, coop);
-                    const V4 *src = st4 + (coop ? fbase : lane);  // own home, or slot 0's while the frame's lanes cooperate
+                    for (; s >= 4; s--) f_layer(s, false);
+                    const V4 *src = st4 + lane;  // own home
                     a3 = f4<real>(ldv(src), ldv(src + 64));
                     b3 = f4<real>(ldv(src + 32), ldv(src + 96));
                 }

@@ -214,3 +214,27 @@ def test_bp_half2_mode_fer(prog, B, ebn0):
     got, flags = eh2.decode_llr(llr)
     assert (((got != u) & (eh2.inI[None, :] > 0)).sum(1) == fe[:64]).all()
     e32.close(); eh2.close()
+
+
+@pytest.mark.parametrize("K", [233, 230, 223, 191, 128, 63, 29, 13, 12, 7])
+def test_frozen_prefix_shapes(K):
+    """The list kernel evaluates the all-frozen prefix as a parallel butterfly (list_decode.cu, "the frozen prefix").  Rates that
+    put the first information bit at 7, 11, 14, 23, 47, 63, 126, 127, 191 and 223 of N = 256 cover: no prefix routine (fewer than
+    two leaf groups), a prefix that is exactly a power of two, one that ends just before the subtree does, and one that
+    reaches into the second half of the frame (capped at N/8 groups, the rest goes through the serial loop)."""
+    from polardecoding_b200 import Engine
+    from polardecoding_b200.capi import preset
+    N, L = 256, 8
+    o = Oracle(None, N=N, K=K, L=L, iters=5)
+    rng = np.random.default_rng(K)
+    u = np.zeros((48, N), dtype=np.int32)
+    u[:, o.I] = rng.integers(0, 2, (48, o.nI))
+    llr = awgn_llr(rng, N, 48, 1.0, encode(u))
+    want, aux = o.decode(llr, kind="scl", L=L)
+    p = preset("SC_128")
+    p.N, p.K, p.decoder, p.list_size = N, K, 1, L
+    eng = Engine(params=p, real="f64")
+    got, flags = eng.decode_llr(llr)
+    assert (got == want).all(), (K, describe(got, want, flags))
+    assert ((flags & 1) == (aux & 1)).all()
+    eng.close()
