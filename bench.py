@@ -117,7 +117,7 @@ def run_reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    fpc = 24                                          # frames per core per step: ~0.2 s of CASCL_1024_L8 on one core
+    fpc = 400                                         # frames per core per step: ~2 s of CASCL_1024_L8 on one core
     for _ in range(a.warmup):
         cpu_arm("CASCL_1024_L8", EBN0_CASCL, 4)
     t0 = time.perf_counter()
@@ -127,7 +127,7 @@ def run_reference_arm(a):
         fps.append(r["fps"])
     ms = (time.perf_counter() - t0) * 1e3 / max(1, a.steps)
     f = sum(fps) / len(fps)
-    rb = cpu_arm("BP_1024", EBN0_BP, 3)
+    rb = cpu_arm("BP_1024", EBN0_BP, 100)
     val = f * K_INFO / 1e9
     line = {"impl": "reference", "metric": "decoded info Gbps: CA-SCL L=8 N=1024 (K=512, CRC-24)", "value": val, "unit": "Gbit/s",
             "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
@@ -138,7 +138,7 @@ def run_reference_arm(a):
             "cpu_baseline": {"value": val, "unit": "Gbit/s", "cores": r["cores"], "kind": r["kind"],
                              "sample": "%d frames per core per step, %d steps, unmodified CASCL() compiled -O2 from the reference source" % (fpc, a.steps)},
             "bp_1024": {"value": rb["fps"] * K_INFO / 1e9, "unit": "Gbit/s", "frames_per_s": rb["fps"], "cores": rb["cores"], "kind": rb["kind"],
-                        "sample": "%d frames per core, BP() 100 sweeps" % 3},
+                        "sample": "%d frames per core, BP() 100 sweeps" % 100},
             "e2e": {"value": val, "unit": "Gbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -293,11 +293,11 @@ def run_gpu_arm(a):
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu:
-        c = cpu_arm("CASCL_1024_L8", EBN0_CASCL, 160)                 # ~1.4 s per core... bounded: ~10-20 s of CPU work in total
-        cb = cpu_arm("BP_1024", EBN0_BP, 6)
+        c = cpu_arm("CASCL_1024_L8", EBN0_CASCL, 2400)                # bounded sample: ~11 s on every core
+        cb = cpu_arm("BP_1024", EBN0_BP, 480)                         # ~10 s on every core
         cpu = {"value": c["fps"] * K_INFO / 1e9, "unit": "Gbit/s", "cores": c["cores"], "kind": c["kind"], "frames_per_s": c["fps"],
-               "sample": "%d frames of CASCL_1024_L8 per core at %.1f dB (%.1f s), unmodified reference CASCL() compiled -O2" % (160, EBN0_CASCL, c["seconds"]),
-               "bp_1024": {"value": cb["fps"] * K_INFO / 1e9, "frames_per_s": cb["fps"], "sample": "6 frames per core, BP() 100 sweeps (%.1f s)" % cb["seconds"]}}
+               "sample": "%d frames of CASCL_1024_L8 per core at %.1f dB (%.1f s), unmodified reference CASCL() compiled -O2" % (2400, EBN0_CASCL, c["seconds"]),
+               "bp_1024": {"value": cb["fps"] * K_INFO / 1e9, "frames_per_s": cb["fps"], "sample": "480 frames per core, BP() 100 sweeps (%.1f s)" % cb["seconds"]}}
     if rank == 0:
         r = res["cascl"]
         line = {"metric": "decoded info Gbps: CA-SCL L=8 N=1024 (K=512, CRC-24)", "value": r["gbps"], "unit": "Gbit/s", "n_gpus": world,
