@@ -213,7 +213,7 @@ def run_gpu_arm(a):
     res = {}
 
     try:
-        traffic_db = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        traffic_db = json.load(open(os.path.join(ROOT, "profiles", "r1b_traffic.json")))
     except Exception:
         traffic_db = {}
 
@@ -260,7 +260,7 @@ def run_gpu_arm(a):
         tr = traffic_db.get(tkey) if tkey else None
         if tr:  # DRAM bytes of this kernel from the committed ncu --set full capture, scaled to this launch's frame count
             out["roofline"]["traffic"] = tr["dram_bytes_per_launch"] * B / tr["frames_per_launch"]
-            out["roofline"]["traffic_source"] = "profiles/r1_traffic.json (ncu dram__bytes_read+write, %d-frame launch)" % tr["frames_per_launch"]
+            out["roofline"]["traffic_source"] = "profiles/r1b_traffic.json (ncu dram__bytes_read+write, %d-frame launch)" % tr["frames_per_launch"]
             out["roofline"]["algorithmic_bytes"] = B * (N * 4 + 2 * (N // 8) + 4)
         assert cnt.frames == world * B * steps_total, (cnt.frames, world, B, steps_total)
         if not e2e:

@@ -21,7 +21,7 @@ for prog, B, snr in (("CASCL_1024_L8", 48, 1.5), ("CASCL_128", 256, 1.5), ("SC_1
     ok &= bad == 0
     print("  parity %%-14s f64: %%d of %%d frames differ" %% (prog, bad, B))
     e.close()
-for prog, real, snr, mult in (("CASCL_1024_L8", "f32", 2.0, 3), ("CASCL_1024_L8", "f64", 2.0, 1), ("SC_1024", "f32", 2.0, 2)):
+for prog, real, snr, mult in (("CASCL_1024_L8", "f32", 2.0, 6), ("CASCL_1024_L8", "f64", 2.0, 1), ("SC_1024", "f32", 2.0, 2)):
     e = Engine(prog, real=real)
     B = int(e.wave_frames()) * mult
     e.simulate_batch(snr, 0, B)
