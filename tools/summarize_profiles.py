@@ -24,6 +24,11 @@ def raw(rep):
     return dict(zip(r[0], r[2] if len(r) > 2 else r[1])), dict(zip(r[0], r[1]))
 
 
+try:  # frames per launch of the profiled command = frames per step of the bench line of the same round
+    _b = json.load(open(os.path.join(ROOT, "gpurun_out", "bench_r1b.json")))
+    FRAMES = {"cascl": _b["config"]["frames_per_step"], "bp": _b["bp_1024"]["frames_per_step"], "bph2": _b["bp_1024"]["frames_per_step"]}
+except Exception:
+    FRAMES = {}
 traffic = {"_note": "dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the kernel inside `python bench.py --steps 2 --warmup 3 --no-cpu`, "
                     "ncu --set full --clock-control none (profiles/%s_*_summary.txt)" % tag}
 for key, title in (("cascl", "CA-SCL N=1024 L=8 fp32 list kernel"), ("bp", "BP N=1024 fp32, 100 sweeps"), ("bph2", "BP N=1024 packed-half mode (optional flag)")):
@@ -43,7 +48,8 @@ for key, title in (("cascl", "CA-SCL N=1024 L=8 fp32 list kernel"), ("bp", "BP N
         return float(x) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[u]
     tot = gb(v["dram__bytes_read.sum"], units["dram__bytes_read.sum"]) + gb(v["dram__bytes_write.sum"], units["dram__bytes_write.sum"])
     traffic[key] = {"kernel": v.get("Kernel Name", ""), "dram_bytes_per_launch": tot, "grid": int(v["launch__grid_size"]),
-                    "time_ms_under_ncu": float(v["gpu__time_duration.sum"]) * {"ms": 1.0, "us": 1e-3, "s": 1e3}.get(units["gpu__time_duration.sum"], 1.0)}
+                    "time_ms_under_ncu": float(v["gpu__time_duration.sum"]) * {"ms": 1.0, "us": 1e-3, "s": 1e3}.get(units["gpu__time_duration.sum"], 1.0),
+                    "frames_per_launch": FRAMES.get(key)}
 json.dump(traffic, open(os.path.join(ROOT, "profiles", "%s_traffic.json" % tag), "w"), indent=1)
 
 # launch list
