@@ -24,6 +24,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: NCCL's banner / debug log (it writes to stdout by default) goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 N, K_INFO = 1024, 512
 OPS_CASCL = 30016 * 27 + 35906 * 2 + 11185 * 11 + 533 * 160 + 36000 + 28000   # ~1.15 M lane-ops / frame
@@ -144,6 +146,26 @@ def run_reference_arm(a):
 
 
 # ------------------------------------------------------------------ GPU arm
+def bind_to_gpu_numa_node(torch, local):
+    """One rank per GPU on a multi-socket host: run on (and first-touch the pinned e2e buffers from) the CPUs next to
+    this rank's GPU, otherwise eight ranks pull their host LLRs through one socket's memory controllers."""
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        cpus = set()
+        for part in open("/sys/bus/pci/devices/%s/local_cpulist" % bdf).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            node = open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip()
+            return {"gpu": bdf, "numa_node": int(node), "cpus": len(cpus)}
+    except Exception:
+        pass
+    return None
+
+
 def timed_steps(torch, dist, world, ext_stream, fn, steps, warmup, count=None):
     for _ in range(warmup):
         fn()
@@ -204,6 +226,7 @@ def run_gpu_arm(a):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(torch, local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pk, pk_src = peaks()
@@ -306,7 +329,8 @@ def run_gpu_arm(a):
                 "config": {"workload": "CASCL_1024_L8 (N=1024 K=512 r=24 L=8) at Eb/N0 %.1f dB, PN-63 payload, Philox AWGN" % EBN0_CASCL,
                            "frames_per_step": r["frames_per_step"], "l2": "inputs larger than L2 (%d MB of LLRs per GPU per step)" % (r["frames_per_step"] // world * N * 4 >> 20),
                            "arith": "fp32 throughput mode; fp64 parity mode is bit-exact with the reference (tests/test_gpu_parity.py)",
-                           "partition": "rank r decodes its own Philox frame range; one NCCL all-reduce of the final counters"},
+                           "partition": "rank r decodes its own Philox frame range; one NCCL all-reduce of the final counters",
+                           "host_numa": numa},
                 "frames_per_s": r["frames_per_s"], "fer": r["fer"], "tie_frames": r["tie_frames"], "frames_counted": r["frames_counted"],
                 "roofline": r["roofline"], "e2e": r["e2e"], "gpu_launches": launches, "clocks": clocks,
                 "bp_1024": {"value": res["bp"]["gbps"], "unit": "Gbit/s", "frames_per_s": res["bp"]["frames_per_s"], "ms_per_step": res["bp"]["ms_per_step"],
