@@ -26,6 +26,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 # stdout carries exactly one JSON line: NCCL's banner / debug log (it writes to stdout by default) goes to stderr
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "WARN"):   # the version banner ignores NCCL_DEBUG_FILE
+    os.environ["NCCL_DEBUG"] = "NONE"
 
 N, K_INFO = 1024, 512
 OPS_CASCL = 30016 * 27 + 35906 * 2 + 11185 * 11 + 533 * 160 + 36000 + 28000   # ~1.15 M lane-ops / frame
