@@ -21,7 +21,18 @@
 #include "engine.h"
 #include "polar_common.cuh"
 
+#ifndef POLAR_BP_KP
+#define POLAR_BP_KP 2  // table steps accumulated packed in the BP kernels' CHK (0 = scalar form); measured 0/1/2/3/5/7 ->
+                       // 0.424/0.419/0.432/0.426/0.422/0.416 Mframes/s at N=1024: BP sits at the FMA-pipe limit, two packed steps balance it
+#endif
+
 namespace polar {
+
+// CHK as the BP kernels use it
+template <typename real> __device__ __forceinline__ real bchk(real a, real b) { return chk<real>(a, b); }
+#if POLAR_BP_KP > 0
+template <> __device__ __forceinline__ float bchk<float>(float a, float b) { return chk_mix_f32<POLAR_BP_KP>(a, b); }
+#endif
 
 template <typename real, int LOGN, int THREADS>
 struct BpCfg {
@@ -110,15 +121,15 @@ __global__ void __launch_bounds__(THREADS) bp_decode_kernel(const BpArgs a)
                     if (i == 0) {  // l(0,.) is not state: form it from l(1,.), r(0,.)
                         ju = 2 * qq; jl = ju + 1;
                         const real lu = Lm[ju], ll = Lm[jl], ru = r0(ju), rl = r0(jl);
-                        su = chk<real>(lu, ll + rl) + ru;
-                        sl = (ll + chk<real>(ru, lu)) + rl;
+                        su = bchk<real>(lu, ll + rl) + ru;
+                        sl = (ll + bchk<real>(ru, lu)) + rl;
                     } else if (i == n) {  // r(n,.) is not state: form it from r(n-1,.), l(n,.) = channel
                         ju = (BPT == 2) ? (2 * tid + e) : qq;  // the positions whose channel LLRs this thread holds
                         jl = ju + N / 2;
                         const real *rin = Rm + (size_t)(n - 2) * N;
                         const real ru = (n == 1) ? r0(ju) : rin[ju], rl = (n == 1) ? r0(jl) : rin[jl];
-                        su = ch_up[e] + chk<real>(ru, ch_lo[e] + rl);
-                        sl = ch_lo[e] + (rl + chk<real>(ru, ch_up[e]));
+                        su = ch_up[e] + bchk<real>(ru, ch_lo[e] + rl);
+                        sl = ch_lo[e] + (rl + bchk<real>(ru, ch_up[e]));
                     } else {
                         ju = 2 * qq; jl = ju + 1;
                         su = Lm[(size_t)(i - 1) * N + ju] + Rm[(size_t)(i - 1) * N + ju];
@@ -158,8 +169,8 @@ __global__ void __launch_bounds__(THREADS) bp_decode_kernel(const BpArgs a)
                     ld2<real>(Lm + j, l0, l1);
                     ld2<real>(Lm + j + 2, l2, l3);
                     const real ra = r0(j), rb = r0(j + 1), rc = r0(j + 2), rd = r0(j + 3);
-                    st2<real>(Rm + j, chk<real>(ra, l1 + rb), rb + chk<real>(ra, l0));
-                    st2<real>(Rm + j + 2, chk<real>(rc, l3 + rd), rd + chk<real>(rc, l2));
+                    st2<real>(Rm + j, bchk<real>(ra, l1 + rb), rb + bchk<real>(ra, l0));
+                    st2<real>(Rm + j + 2, bchk<real>(rc, l3 + rd), rd + bchk<real>(rc, l2));
                     cta_sync<THREADS>();
                 }
                 for (int s = 1; s < n - 1; s++) {
@@ -172,8 +183,8 @@ __global__ void __launch_bounds__(THREADS) bp_decode_kernel(const BpArgs a)
                     ld2<real>(rin + j + d, rl0, rl1);
                     ld2<real>(lin + j, lu0, lu1);
                     ld2<real>(lin + j + d, ll0, ll1);
-                    st2<real>(rout + j, chk<real>(ru0, ll0 + rl0), chk<real>(ru1, ll1 + rl1));
-                    st2<real>(rout + j + d, rl0 + chk<real>(ru0, lu0), rl1 + chk<real>(ru1, lu1));
+                    st2<real>(rout + j, bchk<real>(ru0, ll0 + rl0), bchk<real>(ru1, ll1 + rl1));
+                    st2<real>(rout + j + d, rl0 + bchk<real>(ru0, lu0), rl1 + bchk<real>(ru1, lu1));
                     cta_sync<THREADS>();
                 }
             } else
@@ -189,8 +200,8 @@ __global__ void __launch_bounds__(THREADS) bp_decode_kernel(const BpArgs a)
                     const real ru = (s == 0) ? r0(j) : rin[j];
                     const real rl = (s == 0) ? r0(j + d) : rin[j + d];
                     const real lu = lin[j], ll = lin[j + d];
-                    rout[j] = chk<real>(ru, ll + rl);
-                    rout[j + d] = rl + chk<real>(ru, lu);
+                    rout[j] = bchk<real>(ru, ll + rl);
+                    rout[j + d] = rl + bchk<real>(ru, lu);
                 }
                 cta_sync<THREADS>();
             }
@@ -207,8 +218,8 @@ __global__ void __launch_bounds__(THREADS) bp_decode_kernel(const BpArgs a)
                     else { ld2<real>(lin + j, lu0, lu1); ld2<real>(lin + j + d, ll0, ll1); }
                     ld2<real>(rin + j, ru0, ru1);
                     ld2<real>(rin + j + d, rl0, rl1);
-                    const real ou0 = chk<real>(lu0, ll0 + rl0), ou1 = chk<real>(lu1, ll1 + rl1);
-                    const real ol0 = ll0 + chk<real>(ru0, lu0), ol1 = ll1 + chk<real>(ru1, lu1);
+                    const real ou0 = bchk<real>(lu0, ll0 + rl0), ou1 = bchk<real>(lu1, ll1 + rl1);
+                    const real ol0 = ll0 + bchk<real>(ru0, lu0), ol1 = ll1 + bchk<real>(ru1, lu1);
                     if (a.early_stop) {
                         real pu0, pu1, pl0, pl1;
                         ld2<real>(lout + j, pu0, pu1);
@@ -232,8 +243,8 @@ __global__ void __launch_bounds__(THREADS) bp_decode_kernel(const BpArgs a)
                     const real lu = (s == n - 1) ? ch_up[i] : lin[j];
                     const real ll = (s == n - 1) ? ch_lo[i] : lin[j + d];
                     const real ru = rin[j], rl = rin[j + d];
-                    const real ou = chk<real>(lu, ll + rl);
-                    const real ol = ll + chk<real>(ru, lu);
+                    const real ou = bchk<real>(lu, ll + rl);
+                    const real ol = ll + bchk<real>(ru, lu);
                     if (a.early_stop) changed |= (int)(!RT::same_bits(ou, lout[j])) | (int)(!RT::same_bits(ol, lout[j + d]));
                     lout[j] = ou;
                     lout[j + d] = ol;
@@ -266,8 +277,8 @@ __global__ void __launch_bounds__(THREADS) bp_decode_kernel(const BpArgs a)
                 const real lu = (n == 1) ? ch_up[i] : lin[j];
                 const real ll = (n == 1) ? ch_lo[i] : lin[j + 1];
                 const real ru = r0(j), rl = r0(j + 1);
-                const real ou = chk<real>(lu, ll + rl);
-                const real ol = ll + chk<real>(ru, lu);
+                const real ou = bchk<real>(lu, ll + rl);
+                const real ol = ll + bchk<real>(ru, lu);
                 const uint32_t iu = (a.m.info[j >> 5] >> (j & 31)) & 1u, il = (a.m.info[j >> 5] >> ((j & 31) + 1)) & 1u;
                 const uint32_t bu = (iu && !(ou + ru >= (real)0)) ? 1u : 0u;
                 const uint32_t bl = (il && !(ol + rl >= (real)0)) ? 1u : 0u;

@@ -102,7 +102,7 @@ __device__ __forceinline__ real chk(real a, real b)
 // fp32 CHK with the two table sums accumulated together by packed fp32x2 FMAs (Blackwell FFMA2): 27 instead of 34 issue
 // slots, bit-identical results.  FFMA2 costs ~2.5 FFMA pipe slots (tools/ubench/chk_variants.cu, V7), so this only pays
 // where the issue rate, not the FMA pipe, is the limit: the list decoder gains 5 %, BP (FMA-pipe heavy) loses 2 % -- so
-// list_decode.cu uses chk_lean, bp_decode.cu uses chk.
+// list_decode.cu uses chk_lean, bp_decode.cu uses chk_mix_f32 with two packed steps (below).
 __device__ __forceinline__ unsigned long long pk2(float lo, float hi)
 {
     unsigned long long r;
@@ -127,6 +127,40 @@ __device__ __forceinline__ float chk_lean<float>(float a, float b)
 #undef POLAR_ST
     float ts, td;
     asm("mov.b64 {%0, %1}, %2;" : "=f"(ts), "=f"(td) : "l"(acc));
+    const float m = fminf(fabsf(a), fabsf(b));
+    return real_traits<float>::xsign(m, a, b) + (ts - td);
+}
+
+// Mixed form for kernels that sit between the two limits (BP): the first KP of the seven table steps accumulate packed
+// (one FFMA2 for both sums), the rest scalar.  Same accumulation order, bit-identical results for every KP.
+template <int KP>
+__device__ __forceinline__ float chk_mix_f32(float a, float b)
+{
+    const float NB = -1.152921504606846976e18f, B = 1.152921504606846976e18f;
+    const float s = fabsf(a + b), d = fabsf(a - b);
+    const float T[7] = {4.5f, 2.252f, 1.508f, 1.05f, 0.71f, 0.433f, 0.196f};
+    const int H[7] = {0x3d4ccccd, 0x3dccccce, 0x3dcccccc, 0x3dcccccc, 0x3dcccccc, 0x3dccccd0, 0x3dccccc8};
+    float ts, td;
+    if (KP == 0) {
+        ts = __saturatef(fmaf(s, NB, T[0] * B)) * __int_as_float(H[0]);
+        td = __saturatef(fmaf(d, NB, T[0] * B)) * __int_as_float(H[0]);
+    } else {
+        unsigned long long acc, t = pk2(__saturatef(fmaf(s, NB, T[0] * B)), __saturatef(fmaf(d, NB, T[0] * B)));
+        asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(acc) : "l"(t), "l"(pk2(__int_as_float(H[0]), __int_as_float(H[0]))));
+#pragma unroll
+        for (int k = 1; k < 7; k++)
+            if (k < KP) {
+                t = pk2(__saturatef(fmaf(s, NB, T[k] * B)), __saturatef(fmaf(d, NB, T[k] * B)));
+                asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(t), "l"(pk2(__int_as_float(H[k]), __int_as_float(H[k]))));
+            }
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(ts), "=f"(td) : "l"(acc));
+    }
+#pragma unroll
+    for (int k = 1; k < 7; k++)
+        if (k >= KP) {
+            ts = fmaf(__saturatef(fmaf(s, NB, T[k] * B)), __int_as_float(H[k]), ts);
+            td = fmaf(__saturatef(fmaf(d, NB, T[k] * B)), __int_as_float(H[k]), td);
+        }
     const float m = fminf(fabsf(a), fabsf(b));
     return real_traits<float>::xsign(m, a, b) + (ts - td);
 }
