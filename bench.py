@@ -310,6 +310,7 @@ def run_gpu_arm(a):
     res["cascl"] = bench_one("CASCL_1024_L8", EBN0_CASCL, B_CASCL, OPS_CASCL, tkey="cascl")
     res["bp"] = bench_one("BP_1024", EBN0_BP, B_BP, OPS_BP_SWEEP * 100, tkey="bp")
     res["bp_stop"] = bench_one("BP_1024", EBN0_BP, B_BP, 0, bp_early_stop=1)
+    res["bp_gm"] = bench_one("BP_1024", EBN0_BP, B_BP, 0, e2e=False, bp_early_stop=3)          # optional codeword ("G-matrix") stop rule
     res["bp_h2"] = bench_one("BP_1024", EBN0_BP, B_BP, OPS_BP_SWEEP * 100, real="h2", e2e=False)   # optional packed-half mode (FER-only parity)
     # the bit-exact (fp64) instantiation of both kernels, device-resident inputs only
     res["cascl64"] = bench_one("CASCL_1024_L8", EBN0_CASCL, B_CASCL // 4, OPS_CASCL, real="f64", e2e=False)
@@ -341,6 +342,9 @@ def run_gpu_arm(a):
                             "fixed_point_stop": {"value": res["bp_stop"]["gbps"], "frames_per_s": res["bp_stop"]["frames_per_s"],
                                                  "sweeps_per_frame": res["bp_stop"]["sweeps_per_frame"], "fer": res["bp_stop"]["fer"],
                                                  "roofline": res["bp_stop"]["roofline"], "note": "same decisions as 100 sweeps (bit-exact stop)"},
+                            "gmatrix_stop": {"value": res["bp_gm"]["gbps"], "frames_per_s": res["bp_gm"]["frames_per_s"],
+                                             "sweeps_per_frame": res["bp_gm"]["sweeps_per_frame"], "fer": res["bp_gm"]["fer"],
+                                             "note": "optional flag (bp_early_stop bit 1): stop when the decisions form a codeword; not in the reference, FER-level parity only"},
                             "half2_mode": {"value": res["bp_h2"]["gbps"], "frames_per_s": res["bp_h2"]["frames_per_s"], "fer": res["bp_h2"]["fer"],
                                            "frac_of_fp32_lane_roofline": res["bp_h2"]["roofline"]["frac"],
                                            "note": "PG_REAL_H2, optional flag: two frames per __half2, a numerically different decoder judged on FER only (not the headline)"}}}

@@ -62,7 +62,9 @@ typedef struct pg_params {
     int decoder;           /* enum pg_decoder */
     int list_size;         /* L: 1 (SC) or 2,4,8,16,32 */
     int iter_max;          /* BP sweeps: 100 (BP_1024.c:16); ignored otherwise */
-    int bp_early_stop;     /* 1: stop a frame once a sweep leaves every message bit-identical (decisions unchanged) */
+    int bp_early_stop;     /* bit 0: stop a frame once a sweep leaves every message bit-identical (decisions unchanged, parity-safe);
+                              bit 1: also stop when the hard decisions form a codeword (u G = x, "G-matrix" rule; not in the
+                              reference, FER-level equivalence only; not available with PG_REAL_H2) */
     int real;              /* enum pg_real */
     int data_mode;         /* enum pg_data */
     int count_from;        /* first index of I[] that enters the error count: r for CASCL_1024_sys.c:821, else 0 */

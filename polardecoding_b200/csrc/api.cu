@@ -411,7 +411,7 @@ static int run_decode_on(pg_ctx *ctx, cudaStream_t st, int grid_cap, int cta_off
         a.bpr_E = ctx->bpr_ns ? ctx->d_bpr : nullptr;
         a.bpr_ns = ctx->bpr_ns;
         std::memcpy(a.bpr_samples, ctx->bpr_samples, sizeof(a.bpr_samples));
-        a.B = B; a.iters = p.iter_max; a.early_stop = p.bp_early_stop;
+        a.B = B; a.iters = p.iter_max; a.early_stop = ctx->h2 ? (p.bp_early_stop & 1) : p.bp_early_stop;
         a.m = ctx->masks;
         CU(cudaMemsetAsync(ctx->d_queue, 0, 8, st));
         if (ctx->h2) {

@@ -40,7 +40,7 @@ struct BpCfg {
     static constexpr int W = (N + 31) / 32;
     static constexpr int BPT = (N / 2) / THREADS;  // butterflies per thread per stage
     static constexpr size_t MSG = (size_t)2 * (LOGN - 1) * N;  // l(1..n-1), r(1..n-1)
-    static constexpr size_t SMEM = MSG * sizeof(real) + (size_t)(W + 4) * 4;
+    static constexpr size_t SMEM = MSG * sizeof(real) + (size_t)(2 * W + 4) * 4;  // messages, decisions + 4 words, re-encode check words
 };
 
 // two neighbouring messages as one 64/128-bit shared-memory access
@@ -80,7 +80,8 @@ __global__ void __launch_bounds__(THREADS) bp_decode_kernel(const BpArgs a)
     real *Rm = Lm + (size_t)(n - 1) * N;                  // Rm[(s-1)*N + j] = r(s,j), s=1..n-1
     uint32_t *uh = reinterpret_cast<uint32_t *>(smem_raw + C::MSG * sizeof(real));  // W words + [W]=nerr, [W+1]=frame lo, [W+2]=frame hi
     // BPR statistic (only when a.bpr_ns > 0; the launch then adds N + 8*16*4 bytes): one byte per position, per-CTA counters
-    uint8_t *bb = reinterpret_cast<uint8_t *>(uh + W + 4);
+    uint32_t *xh = uh + W + 4;  // hard decisions on the channel side (G-matrix stop)
+    uint8_t *bb = reinterpret_cast<uint8_t *>(xh + W);
     uint32_t *bE = reinterpret_cast<uint32_t *>(bb + N);
     const int tid = threadIdx.x;
 
@@ -157,6 +158,48 @@ __global__ void __launch_bounds__(THREADS) bp_decode_kernel(const BpArgs a)
             }
         };
 
+        // Optional stop rule (a.early_stop & 2; NOT in the reference, judged on FER only): after a sweep, decide u from
+        // l(0,.)+r(0,.) and x from l(n,.)+r(n,.) and stop when u G = x, i.e. when the decisions form a codeword.  Costs the two
+        // stage passes the plain sweep skips (l(0) and r(n)) plus a packed re-encode by one warp.
+        auto gmatrix_ok = [&]() -> bool {
+            if (tid < W) { uh[tid] = 0; xh[tid] = 0; }
+            cta_sync<THREADS>();
+            const real *rin = Rm + (size_t)(n - 2) * N;  // r(n-1,.)
+#pragma unroll
+            for (int i = 0; i < BPT; i++) {
+                {   // u side: the positions 2q, 2q+1
+                    const int q = tid + i * THREADS, j = 2 * q;
+                    const real lu = Lm[j], ll = Lm[j + 1], ru = r0(j), rl = r0(j + 1);
+                    const real ou = bchk<real>(lu, ll + rl), ol = ll + bchk<real>(ru, lu);
+                    const uint32_t iu = (a.m.info[j >> 5] >> (j & 31)) & 1u, il = (a.m.info[j >> 5] >> ((j & 31) + 1)) & 1u;
+                    const uint32_t two = ((iu && !(ou + ru >= (real)0)) ? 1u : 0u) | ((il && !(ol + rl >= (real)0)) ? 2u : 0u);
+                    if (two) atomicOr(&uh[j >> 5], two << (j & 31));
+                }
+                {   // x side: the positions whose channel LLRs this thread holds
+                    const int ju = (BPT == 2) ? (2 * tid + i) : (tid + i * THREADS), jl = ju + N / 2;
+                    const real ru = rin[ju], rl = rin[jl];
+                    const real su = ch_up[i] + bchk<real>(ru, ch_lo[i] + rl);
+                    const real sl = ch_lo[i] + (rl + bchk<real>(ru, ch_up[i]));
+                    if (!(su >= (real)0)) atomicOr(&xh[ju >> 5], 1u << (ju & 31));
+                    if (!(sl >= (real)0)) atomicOr(&xh[jl >> 5], 1u << (jl & 31));
+                }
+            }
+            cta_sync<THREADS>();
+            if (tid < 32) {  // x' = u F^{(x)n} on packed words, one word per lane
+                uint32_t w = (tid < W) ? polar_word_stages(uh[tid]) : 0u;
+#pragma unroll
+                for (int d = 1; d < W; d <<= 1) {
+                    const uint32_t o = __shfl_xor_sync(0xffffffffu, w, d);
+                    if (!(tid & d)) w ^= o;
+                }
+                const int bad = (tid < W) && (w != xh[tid]);
+                const int any = __any_sync(0xffffffffu, bad);
+                if (tid == 0) uh[W + 3] = any ? 0u : 1u;
+            }
+            cta_sync<THREADS>();
+            return uh[W + 3] != 0u;
+        };
+
         int sweeps = 0;
         for (int it = 0; it < a.iters; it++) {
             // ---- R pass, stages 0..n-2 (stage n-1 would only produce r(n), which nothing reads)
@@ -220,7 +263,7 @@ __global__ void __launch_bounds__(THREADS) bp_decode_kernel(const BpArgs a)
                     ld2<real>(rin + j + d, rl0, rl1);
                     const real ou0 = bchk<real>(lu0, ll0 + rl0), ou1 = bchk<real>(lu1, ll1 + rl1);
                     const real ol0 = ll0 + bchk<real>(ru0, lu0), ol1 = ll1 + bchk<real>(ru1, lu1);
-                    if (a.early_stop) {
+                    if (a.early_stop & 1) {
                         real pu0, pu1, pl0, pl1;
                         ld2<real>(lout + j, pu0, pu1);
                         ld2<real>(lout + j + d, pl0, pl1);
@@ -245,7 +288,7 @@ __global__ void __launch_bounds__(THREADS) bp_decode_kernel(const BpArgs a)
                     const real ru = rin[j], rl = rin[j + d];
                     const real ou = bchk<real>(lu, ll + rl);
                     const real ol = ll + bchk<real>(ru, lu);
-                    if (a.early_stop) changed |= (int)(!RT::same_bits(ou, lout[j])) | (int)(!RT::same_bits(ol, lout[j + d]));
+                    if (a.early_stop & 1) changed |= (int)(!RT::same_bits(ou, lout[j])) | (int)(!RT::same_bits(ol, lout[j + d]));
                     lout[j] = ou;
                     lout[j + d] = ol;
                 }
@@ -255,10 +298,15 @@ __global__ void __launch_bounds__(THREADS) bp_decode_kernel(const BpArgs a)
             if (a.bpr_ns && a.truth)
                 for (int q = 0; q < a.bpr_ns; q++)
                     if (a.bpr_samples[q] == sweeps) bpr_sample(q);
-            if (a.early_stop) {
+            if (a.early_stop & 1) {
                 const int any = (THREADS == 32) ? __any_sync(0xffffffffu, changed) : __syncthreads_or(changed);
                 if (!any) break;
             }
+            if ((a.early_stop & 2) && n >= 2 && gmatrix_ok()) break;
+        }
+        if (a.early_stop & 2) {  // the decision words are rebuilt below from the same state
+            if (tid < W) uh[tid] = 0;
+            cta_sync<THREADS>();
         }
         if (a.bpr_ns && a.truth) {  // samples scheduled after a fixed-point stop see the same, final, state
             for (int q = 0; q < a.bpr_ns; q++)

@@ -19,6 +19,7 @@
  *                                   reference's order, so that run/error columns reproduce its captures exactly
  *   --real f32|f64                  arithmetic (default f32 with philox, f64 with ref)
  *   --L n  --iters n  --early-stop  list size / BP sweeps / bit-exact fixed-point stop
+ *   --gmatrix-stop                  BP: also stop when the decisions form a codeword (not in the reference; same FER, fewer sweeps)
  *   --gpus n                        partition the frame space over n GPUs (one forked process + one ctx per GPU, NCCL counters)
  *   --verbose                       throughput and tie/CRC statistics on stderr (stdout stays drop-in)
  */
@@ -325,7 +326,8 @@ int main(int argc, char **argv)
         else if (!strcmp(a, "--L") && v) { L = atol(v); i++; }
         else if (!strcmp(a, "--iters") && v) { iters = atol(v); i++; }
         else if (!strcmp(a, "--gpus") && v) { gpus = atol(v); i++; }
-        else if (!strcmp(a, "--early-stop")) early = 1;
+        else if (!strcmp(a, "--early-stop")) early |= 1;
+        else if (!strcmp(a, "--gmatrix-stop")) early |= 2;
         else if (!strcmp(a, "--verbose")) verbose = 1;
         else { fprintf(stderr, "polar_sim: unknown option %s\n", a); return 2; }
     }
