@@ -522,7 +522,11 @@ static int decode_host(pg_ctx *ctx, const void *llr, int llr_is_f64, size_t B, u
     if (const char *e = getenv("POLARGPU_LANES")) lanes = std::max(1, std::min(kPipeLanes, atoi(e)));  // tuning aid
     if (ctx->p.decoder == PG_DEC_BP || ctx->grid < lanes) lanes = 1;
     const int nbuf = 2 * lanes, lane_grid = ctx->grid / lanes;
-    const size_t pc = std::min<size_t>(ctx->chunk_max, std::max<size_t>((size_t)wave_frames(ctx) / lanes, 1024));
+    // BP frames come from a device-side queue (no tail imbalance), and a wave is only a few hundred frames: several waves per chunk
+    size_t bp_waves = 8;
+    if (const char *e = getenv("POLARGPU_BP_CHUNK_WAVES")) bp_waves = (size_t)std::max(1, atoi(e));  // tuning aid
+    const size_t per_launch = (ctx->p.decoder == PG_DEC_BP) ? (size_t)wave_frames(ctx) * bp_waves : (size_t)wave_frames(ctx) / lanes;
+    const size_t pc = std::min<size_t>(ctx->chunk_max, std::max<size_t>(per_launch, 1024));
     if (B > pc && !getenv("POLARGPU_NO_PIPELINE")) {
         int rc = ensure_pipe(ctx, pc, u_hat != nullptr);
         if (rc) return rc;
