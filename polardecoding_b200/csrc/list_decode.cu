@@ -12,22 +12,27 @@
 //    unrolled layers.  Slots that hold no path yet (list filling) carry PM=+inf and are exact copies
 //    of path 0, so they compute finite values and never win a comparison.
 //  * Array formulation: at bit j, t=ctz(j): one g-layer at stage t then f-layers t-1..0; stage s keeps
-//    2^s live LLRs.  Stages 0..1 live in registers, stages
-//    2..SMEM_TOP-1 in shared memory, the rest in an L2-resident global scratch, all laid out
+//    2^s live LLRs.  Stages 0..2 live in registers only (stage 2 feeds the four leaves of its group and
+//    is cloned by shuffle), stage 3 goes through registers to the f step below it and is also stored,
+//    stages 3..SMEM_TOP-1 are in shared memory, the rest in an L2/HBM global scratch, all laid out
 //    [idx/4][lane][4] so that a warp's 128-bit accesses are contiguous/conflict-free.
 //  * Lazy copy: every path owns a HOME array per stage and a packed pointer word saying where its
 //    current stage-s data lives.  Stage s is rewritten by all paths at the same bits (multiples of
 //    2^s), always into the home array, so a clone is a register shuffle of the pointer word -- the
 //    reference copies the whole graph instead (copyPath/simpleCopy, 74 % of its run time).
+//    Only the first layer of a chain (the g-layer) follows a pointer; the f-layers below it read what
+//    their own lane just wrote, and the pointer fields of the whole chain are merged in once at its end.
 //  * Partial sums are kept as packed bit vectors per stage (B[s], 2^s bits) with the same pointer
 //    scheme; stages 2..5 are registers, 6..BITS_TOP-1 shared memory, the rest global scratch.
 //    The final B[n] is the re-encoded codeword, u_hat = B[n] F^{(x)n}.
-//  * Code size matters: with ~13 single-warp CTAs per SM at unrelated program counters the first version
+//  * The all-frozen prefix (one path, every decision 0) has no data dependence: the frame's L lanes
+//    evaluate it as a parallel butterfly and add the leaf penalties in leaf order (see "the frozen prefix").
+//  * Code size matters: the warps of an SM sit at unrelated program counters.  The first version
 //    (64-90 KB of SASS, everything unrolled) spent most issue slots waiting for instruction fetch
-//    (ncu: stall_no_instruction 4.0 per issue, profiles/r1_cascl_v1_summary.txt).  The hot loop is now one
-//    f-layer body, one g-layer body and one leaf body, looped rather than unrolled.
-//  * List pruning: each lane ranks its two candidates against the 2L candidates of its frame with
-//    shuffles.  If all candidates are distinct (checked with one warp reduction) rank < L is exactly
+//    (ncu: stall_no_instruction 4.0 per issue, profiles/r1_cascl_v1_summary.txt).  The hot loop is a few
+//    looped bodies (generic f/g layers, the stage-3/2 steps, two leaf bodies): ~50 KB, stall 0.5-1.2.
+//  * List pruning: lo = L-th and hi = (L+1)-th smallest of the frame's 2L candidates from a bitonic
+//    merge network on shuffles (see leaf()).  If lo < hi in every frame of the warp, "PM < hi" is exactly
 //    the reference's "PM < med"; otherwise (exact ties, or +inf slots while the list fills) a slow
 //    path applies the total order (value, candidate index) and flags frames where the reference's
 //    rule would have been ambiguous ("Oops!", SCL_1024.c:621).
