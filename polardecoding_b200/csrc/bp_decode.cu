@@ -30,8 +30,11 @@ namespace polar {
 
 // CHK as the BP kernels use it
 template <typename real> __device__ __forceinline__ real bchk(real a, real b) { return chk<real>(a, b); }
-#if POLAR_BP_KP > 0
-template <> __device__ __forceinline__ float bchk<float>(float a, float b) { return chk_mix_f32<POLAR_BP_KP>(a, b); }
+#ifndef POLAR_BP_KM
+#define POLAR_BP_KM 0  // table steps whose indicators come from the ALU pipe (FSET) instead of the FMA pipe (FFMA.SAT)
+#endif
+#if POLAR_BP_KP > 0 || POLAR_BP_KM > 0
+template <> __device__ __forceinline__ float bchk<float>(float a, float b) { return chk_mix_f32<POLAR_BP_KP, POLAR_BP_KM>(a, b); }
 #endif
 
 template <typename real, int LOGN, int THREADS>

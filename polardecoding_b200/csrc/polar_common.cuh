@@ -131,35 +131,46 @@ __device__ __forceinline__ float chk_lean<float>(float a, float b)
     return real_traits<float>::xsign(m, a, b) + (ts - td);
 }
 
-// Mixed form for kernels that sit between the two limits (BP): the first KP of the seven table steps accumulate packed
-// (one FFMA2 for both sums), the rest scalar.  Same accumulation order, bit-identical results for every KP.
-template <int KP>
+// Balanced form for kernels that sit near several limits at once (BP: issue slots, FMA pipe, ALU pipe).  Per table step
+// the indicator [x < t] comes either from the FMA pipe (FFMA.SAT, as above) or from the ALU pipe (FSET.BF, the first KM steps),
+// and the two sums accumulate packed (one FFMA2 for both, the first KP steps) or scalar.  Every choice gives exactly 1.0f/0.0f
+// indicators and the same accumulation order, so the results are bit-identical for all (KP, KM).
+__device__ __forceinline__ float step_alu(float x, float t)
+{
+    float r;
+    asm("set.lt.f32.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(t));
+    return r;
+}
+template <int KP, int KM>
 __device__ __forceinline__ float chk_mix_f32(float a, float b)
 {
     const float NB = -1.152921504606846976e18f, B = 1.152921504606846976e18f;
     const float s = fabsf(a + b), d = fabsf(a - b);
     const float T[7] = {4.5f, 2.252f, 1.508f, 1.05f, 0.71f, 0.433f, 0.196f};
     const int H[7] = {0x3d4ccccd, 0x3dccccce, 0x3dcccccc, 0x3dcccccc, 0x3dcccccc, 0x3dccccd0, 0x3dccccc8};
+    float hs[7], hd[7];
+#pragma unroll
+    for (int k = 0; k < 7; k++) {
+        hs[k] = (k < KM) ? step_alu(s, T[k]) : __saturatef(fmaf(s, NB, T[k] * B));
+        hd[k] = (k < KM) ? step_alu(d, T[k]) : __saturatef(fmaf(d, NB, T[k] * B));
+    }
     float ts, td;
     if (KP == 0) {
-        ts = __saturatef(fmaf(s, NB, T[0] * B)) * __int_as_float(H[0]);
-        td = __saturatef(fmaf(d, NB, T[0] * B)) * __int_as_float(H[0]);
+        ts = hs[0] * __int_as_float(H[0]);
+        td = hd[0] * __int_as_float(H[0]);
     } else {
-        unsigned long long acc, t = pk2(__saturatef(fmaf(s, NB, T[0] * B)), __saturatef(fmaf(d, NB, T[0] * B)));
-        asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(acc) : "l"(t), "l"(pk2(__int_as_float(H[0]), __int_as_float(H[0]))));
+        unsigned long long acc;
+        asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(acc) : "l"(pk2(hs[0], hd[0])), "l"(pk2(__int_as_float(H[0]), __int_as_float(H[0]))));
 #pragma unroll
         for (int k = 1; k < 7; k++)
-            if (k < KP) {
-                t = pk2(__saturatef(fmaf(s, NB, T[k] * B)), __saturatef(fmaf(d, NB, T[k] * B)));
-                asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(t), "l"(pk2(__int_as_float(H[k]), __int_as_float(H[k]))));
-            }
+            if (k < KP) asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(pk2(hs[k], hd[k])), "l"(pk2(__int_as_float(H[k]), __int_as_float(H[k]))));
         asm("mov.b64 {%0, %1}, %2;" : "=f"(ts), "=f"(td) : "l"(acc));
     }
 #pragma unroll
     for (int k = 1; k < 7; k++)
         if (k >= KP) {
-            ts = fmaf(__saturatef(fmaf(s, NB, T[k] * B)), __int_as_float(H[k]), ts);
-            td = fmaf(__saturatef(fmaf(d, NB, T[k] * B)), __int_as_float(H[k]), td);
+            ts = fmaf(hs[k], __int_as_float(H[k]), ts);
+            td = fmaf(hd[k], __int_as_float(H[k]), td);
         }
     const float m = fminf(fabsf(a), fabsf(b));
     return real_traits<float>::xsign(m, a, b) + (ts - td);
