@@ -21,18 +21,22 @@
 #include "engine.h"
 #include "polar_common.cuh"
 
+// CHK as the BP kernels use it: BP sits near three limits at once (issue slots, FMA pipe, ALU pipe), so the table steps are
+// split between the pipes: all seven accumulate packed (FFMA2: fewer issue slots, more FMA-pipe time) and the indicators of the
+// first four come from the ALU pipe (FSET) instead of the FMA pipe (FFMA.SAT).  Bit-identical for every choice; measured at
+// N=1024, Mframes/s for (packed, ALU) = (0,0) 0.424, (2,0) 0.432/0.4385, (6,3) 0.443, (7,3) 0.431, (7,4) 0.446, (7,5) 0.440,
+// (7,7) 0.405 (tools/ab_bp.py; the two (2,0) figures are two boxes).
 #ifndef POLAR_BP_KP
-#define POLAR_BP_KP 2  // table steps accumulated packed in the BP kernels' CHK (0 = scalar form); measured 0/1/2/3/5/7 ->
-                       // 0.424/0.419/0.432/0.426/0.422/0.416 Mframes/s at N=1024: BP sits at the FMA-pipe limit, two packed steps balance it
+#define POLAR_BP_KP 7
+#endif
+#ifndef POLAR_BP_KM
+#define POLAR_BP_KM 4
 #endif
 
 namespace polar {
 
 // CHK as the BP kernels use it
 template <typename real> __device__ __forceinline__ real bchk(real a, real b) { return chk<real>(a, b); }
-#ifndef POLAR_BP_KM
-#define POLAR_BP_KM 0  // table steps whose indicators come from the ALU pipe (FSET) instead of the FMA pipe (FFMA.SAT)
-#endif
 #if POLAR_BP_KP > 0 || POLAR_BP_KM > 0
 template <> __device__ __forceinline__ float bchk<float>(float a, float b) { return chk_mix_f32<POLAR_BP_KP, POLAR_BP_KM>(a, b); }
 #endif
