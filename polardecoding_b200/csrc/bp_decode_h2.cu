@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(THREADS) bp_decode_h2_kernel(const BpArgs a)
                 st2h(Rm + j + 2, chk_h2(rc, __hadd2(l3, rd)), __hadd2(rd, chk_h2(rc, l2)));
                 cta_sync_h2<THREADS>();
             }
+#pragma unroll
             for (int s = 1; s < n - 1; s++) {
                 const int d = 1 << s, q = 2 * tid;
                 const int j = ((q >> s) << (s + 1)) | (q & (d - 1));
@@ -130,6 +131,7 @@ __global__ void __launch_bounds__(THREADS) bp_decode_h2_kernel(const BpArgs a)
                 cta_sync_h2<THREADS>();
             }
             int changed = 0;
+#pragma unroll
             for (int s = n - 1; s >= 1; s--) {
                 const int d = 1 << s, q = 2 * tid;
                 const int j = ((q >> s) << (s + 1)) | (q & (d - 1));
