@@ -240,6 +240,7 @@ __global__ void __launch_bounds__(THREADS) bp_decode_kernel(const BpArgs a)
                     cta_sync<THREADS>();
                 }
             } else
+#pragma unroll
             for (int s = 0; s < n - 1; s++) {
                 const int d = 1 << s;
                 const real *rin = Rm + (size_t)(s - 1) * N;
@@ -284,6 +285,7 @@ __global__ void __launch_bounds__(THREADS) bp_decode_kernel(const BpArgs a)
                     cta_sync<THREADS>();
                 }
             } else
+#pragma unroll
             for (int s = n - 1; s >= 1; s--) {
                 const int d = 1 << s;
                 const real *rin = Rm + (size_t)(s - 1) * N;  // r(s,.)
