@@ -67,6 +67,13 @@ __device__ __forceinline__ void st2(real *p, real a, real b)
     *reinterpret_cast<typename pair_t<real>::type *>(p) = v;
 }
 
+// the same through 32-bit shared-window addresses (the generic-pointer form makes the compiler rebuild the window base --
+// S2UR + UMOV + ULEA -- in every stage: 6 of ~140 instructions per stage pass)
+__device__ __forceinline__ void lds2(uint32_t a, float &x, float &y) { asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(x), "=f"(y) : "r"(a) : "memory"); }
+__device__ __forceinline__ void lds2(uint32_t a, double &x, double &y) { asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(a) : "memory"); }
+__device__ __forceinline__ void sts2(uint32_t a, float x, float y) { asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(x), "f"(y) : "memory"); }
+__device__ __forceinline__ void sts2(uint32_t a, double x, double y) { asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(x), "d"(y) : "memory"); }
+
 template <int THREADS>
 __device__ __forceinline__ void cta_sync()
 {
@@ -91,6 +98,17 @@ __global__ void __launch_bounds__(THREADS) bp_decode_kernel(const BpArgs a)
     uint8_t *bb = reinterpret_cast<uint8_t *>(xh + W);
     uint32_t *bE = reinterpret_cast<uint32_t *>(bb + N);
     const int tid = threadIdx.x;
+#ifndef POLAR_BP_GENERIC_SMEM
+    uint32_t sa = (uint32_t)__cvta_generic_to_shared(Lm);  // message index i (l at i, r at RO + i) lives at sa + i*sizeof(real)
+    asm volatile("mov.b32 %0, %0;" : "+r"(sa));                 // opaque: keep it in a register instead of rebuilding it per stage
+    constexpr int RO = (LOGN - 1) * N;
+    auto LD = [&](int i, real &x, real &y) { lds2(sa + (uint32_t)i * (uint32_t)sizeof(real), x, y); };
+    auto ST = [&](int i, real x, real y) { sts2(sa + (uint32_t)i * (uint32_t)sizeof(real), x, y); };
+#else
+    constexpr int RO = (LOGN - 1) * N;
+    auto LD = [&](int i, real &x, real &y) { ld2<real>(Lm + i, x, y); };
+    auto ST = [&](int i, real x, real y) { st2<real>(Lm + i, x, y); };
+#endif
 
     auto r0 = [&](int j) -> real { return ((a.m.info[j >> 5] >> (j & 31)) & 1u) ? (real)0 : (real)999; };
 
@@ -216,11 +234,11 @@ __global__ void __launch_bounds__(THREADS) bp_decode_kernel(const BpArgs a)
                 {   // s = 0: butterflies (4t,4t+1) and (4t+2,4t+3)
                     const int j = 4 * tid;
                     real l0, l1, l2, l3;
-                    ld2<real>(Lm + j, l0, l1);
-                    ld2<real>(Lm + j + 2, l2, l3);
+                    LD(j, l0, l1);
+                    LD(j + 2, l2, l3);
                     const real ra = r0(j), rb = r0(j + 1), rc = r0(j + 2), rd = r0(j + 3);
-                    st2<real>(Rm + j, bchk<real>(ra, l1 + rb), rb + bchk<real>(ra, l0));
-                    st2<real>(Rm + j + 2, bchk<real>(rc, l3 + rd), rd + bchk<real>(rc, l2));
+                    ST(RO + j, bchk<real>(ra, l1 + rb), rb + bchk<real>(ra, l0));
+                    ST(RO + j + 2, bchk<real>(rc, l3 + rd), rd + bchk<real>(rc, l2));
                     cta_sync<THREADS>();
                 }
 #pragma unroll  // compile-time stage: strides, masks and array offsets become immediates (+4 % at N=1024; the CTAs of an SM run in
@@ -228,15 +246,14 @@ __global__ void __launch_bounds__(THREADS) bp_decode_kernel(const BpArgs a)
                 for (int s = 1; s < n - 1; s++) {
                     const int d = 1 << s, q = 2 * tid;
                     const int j = ((q >> s) << (s + 1)) | (q & (d - 1));
-                    const real *rin = Rm + (size_t)(s - 1) * N, *lin = Lm + (size_t)s * N;
-                    real *rout = Rm + (size_t)s * N;
+                    const int rin = RO + (s - 1) * N + j, lin = s * N + j, rout = RO + s * N + j;
                     real ru0, ru1, rl0, rl1, lu0, lu1, ll0, ll1;
-                    ld2<real>(rin + j, ru0, ru1);
-                    ld2<real>(rin + j + d, rl0, rl1);
-                    ld2<real>(lin + j, lu0, lu1);
-                    ld2<real>(lin + j + d, ll0, ll1);
-                    st2<real>(rout + j, bchk<real>(ru0, ll0 + rl0), bchk<real>(ru1, ll1 + rl1));
-                    st2<real>(rout + j + d, rl0 + bchk<real>(ru0, lu0), rl1 + bchk<real>(ru1, lu1));
+                    LD(rin, ru0, ru1);
+                    LD(rin + d, rl0, rl1);
+                    LD(lin, lu0, lu1);
+                    LD(lin + d, ll0, ll1);
+                    ST(rout, bchk<real>(ru0, ll0 + rl0), bchk<real>(ru1, ll1 + rl1));
+                    ST(rout + d, rl0 + bchk<real>(ru0, lu0), rl1 + bchk<real>(ru1, lu1));
                     cta_sync<THREADS>();
                 }
             } else
@@ -265,23 +282,22 @@ __global__ void __launch_bounds__(THREADS) bp_decode_kernel(const BpArgs a)
                 for (int s = n - 1; s >= 1; s--) {
                     const int d = 1 << s, q = 2 * tid;
                     const int j = ((q >> s) << (s + 1)) | (q & (d - 1));
-                    const real *rin = Rm + (size_t)(s - 1) * N, *lin = Lm + (size_t)s * N;
-                    real *lout = Lm + (size_t)(s - 1) * N;
+                    const int rin = RO + (s - 1) * N + j, lin = s * N + j, lout = (s - 1) * N + j;
                     real ru0, ru1, rl0, rl1, lu0, lu1, ll0, ll1;
                     if (s == n - 1) { lu0 = ch_up[0]; lu1 = ch_up[1]; ll0 = ch_lo[0]; ll1 = ch_lo[1]; }
-                    else { ld2<real>(lin + j, lu0, lu1); ld2<real>(lin + j + d, ll0, ll1); }
-                    ld2<real>(rin + j, ru0, ru1);
-                    ld2<real>(rin + j + d, rl0, rl1);
+                    else { LD(lin, lu0, lu1); LD(lin + d, ll0, ll1); }
+                    LD(rin, ru0, ru1);
+                    LD(rin + d, rl0, rl1);
                     const real ou0 = bchk<real>(lu0, ll0 + rl0), ou1 = bchk<real>(lu1, ll1 + rl1);
                     const real ol0 = ll0 + bchk<real>(ru0, lu0), ol1 = ll1 + bchk<real>(ru1, lu1);
                     if (a.early_stop & 1) {
                         real pu0, pu1, pl0, pl1;
-                        ld2<real>(lout + j, pu0, pu1);
-                        ld2<real>(lout + j + d, pl0, pl1);
+                        LD(lout, pu0, pu1);
+                        LD(lout + d, pl0, pl1);
                         changed |= (int)(!RT::same_bits(ou0, pu0)) | (int)(!RT::same_bits(ou1, pu1)) | (int)(!RT::same_bits(ol0, pl0)) | (int)(!RT::same_bits(ol1, pl1));
                     }
-                    st2<real>(lout + j, ou0, ou1);
-                    st2<real>(lout + j + d, ol0, ol1);
+                    ST(lout, ou0, ou1);
+                    ST(lout + d, ol0, ol1);
                     cta_sync<THREADS>();
                 }
             } else

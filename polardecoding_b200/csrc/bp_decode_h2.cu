@@ -48,6 +48,17 @@ __device__ __forceinline__ void st2h(__half2 *p, __half2 x, __half2 y)
     h2x2 v; v.a = x; v.b = y;
     *reinterpret_cast<h2x2 *>(p) = v;
 }
+// the same through 32-bit shared-window addresses (see bp_decode.cu: keeps the window base out of every stage)
+__device__ __forceinline__ void lds2h(uint32_t a, __half2 &x, __half2 &y)
+{
+    uint32_t u, v;
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(u), "=r"(v) : "r"(a) : "memory");
+    x = *reinterpret_cast<const __half2 *>(&u); y = *reinterpret_cast<const __half2 *>(&v);
+}
+__device__ __forceinline__ void sts2h(uint32_t a, __half2 x, __half2 y)
+{
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a), "r"(*reinterpret_cast<const uint32_t *>(&x)), "r"(*reinterpret_cast<const uint32_t *>(&y)) : "memory");
+}
 __device__ __forceinline__ uint32_t bits_of(__half2 v) { return *reinterpret_cast<const uint32_t *>(&v); }
 
 template <int THREADS>
@@ -73,10 +84,15 @@ __global__ void __launch_bounds__(THREADS) bp_decode_h2_kernel(const BpArgs a)
     constexpr int N = C::N, W = C::W, n = LOGN;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __half2 *Lm = reinterpret_cast<__half2 *>(smem_raw);  // Lm[(s-1)*N + j] = l(s,j) of frames (A,B)
-    __half2 *Rm = Lm + (size_t)(n - 1) * N;
+    // r(s,j) follows at Lm[(n-1)*N + (s-1)*N + j] (RO below)
     uint32_t *uh = reinterpret_cast<uint32_t *>(smem_raw + C::MSG * sizeof(__half2));  // [0,W) frame A, [W,2W) frame B, then scratch words
     const int tid = threadIdx.x;
     const unsigned long long pairs = (a.B + 1) / 2;
+    uint32_t sa = (uint32_t)__cvta_generic_to_shared(Lm);  // message index i (l at i, r at RO + i) lives at sa + 4 i
+    asm volatile("mov.b32 %0, %0;" : "+r"(sa));                 // opaque: stays in a register
+    constexpr int RO = (LOGN - 1) * N;
+    auto LD = [&](int i, __half2 &x, __half2 &y) { lds2h(sa + 4u * (uint32_t)i, x, y); };
+    auto ST = [&](int i, __half2 x, __half2 y) { sts2h(sa + 4u * (uint32_t)i, x, y); };
 
     auto r0 = [&](int j) -> __half2 { return ((a.m.info[j >> 5] >> (j & 31)) & 1u) ? h2c(0.f) : h2c(999.f); };
 
@@ -108,26 +124,25 @@ __global__ void __launch_bounds__(THREADS) bp_decode_h2_kernel(const BpArgs a)
             {   // R pass, s = 0
                 const int j = 4 * tid;
                 __half2 l0, l1, l2, l3;
-                ld2h(Lm + j, l0, l1);
-                ld2h(Lm + j + 2, l2, l3);
+                LD(j, l0, l1);
+                LD(j + 2, l2, l3);
                 const __half2 ra = r0(j), rb = r0(j + 1), rc = r0(j + 2), rd = r0(j + 3);
-                st2h(Rm + j, chk_h2(ra, __hadd2(l1, rb)), __hadd2(rb, chk_h2(ra, l0)));
-                st2h(Rm + j + 2, chk_h2(rc, __hadd2(l3, rd)), __hadd2(rd, chk_h2(rc, l2)));
+                ST(RO + j, chk_h2(ra, __hadd2(l1, rb)), __hadd2(rb, chk_h2(ra, l0)));
+                ST(RO + j + 2, chk_h2(rc, __hadd2(l3, rd)), __hadd2(rd, chk_h2(rc, l2)));
                 cta_sync_h2<THREADS>();
             }
 #pragma unroll
             for (int s = 1; s < n - 1; s++) {
                 const int d = 1 << s, q = 2 * tid;
                 const int j = ((q >> s) << (s + 1)) | (q & (d - 1));
-                const __half2 *rin = Rm + (size_t)(s - 1) * N, *lin = Lm + (size_t)s * N;
-                __half2 *rout = Rm + (size_t)s * N;
+                const int rin = RO + (s - 1) * N + j, lin = s * N + j, rout = RO + s * N + j;
                 __half2 ru0, ru1, rl0, rl1, lu0, lu1, ll0, ll1;
-                ld2h(rin + j, ru0, ru1);
-                ld2h(rin + j + d, rl0, rl1);
-                ld2h(lin + j, lu0, lu1);
-                ld2h(lin + j + d, ll0, ll1);
-                st2h(rout + j, chk_h2(ru0, __hadd2(ll0, rl0)), chk_h2(ru1, __hadd2(ll1, rl1)));
-                st2h(rout + j + d, __hadd2(rl0, chk_h2(ru0, lu0)), __hadd2(rl1, chk_h2(ru1, lu1)));
+                LD(rin, ru0, ru1);
+                LD(rin + d, rl0, rl1);
+                LD(lin, lu0, lu1);
+                LD(lin + d, ll0, ll1);
+                ST(rout, chk_h2(ru0, __hadd2(ll0, rl0)), chk_h2(ru1, __hadd2(ll1, rl1)));
+                ST(rout + d, __hadd2(rl0, chk_h2(ru0, lu0)), __hadd2(rl1, chk_h2(ru1, lu1)));
                 cta_sync_h2<THREADS>();
             }
             int changed = 0;
@@ -135,23 +150,22 @@ __global__ void __launch_bounds__(THREADS) bp_decode_h2_kernel(const BpArgs a)
             for (int s = n - 1; s >= 1; s--) {
                 const int d = 1 << s, q = 2 * tid;
                 const int j = ((q >> s) << (s + 1)) | (q & (d - 1));
-                const __half2 *rin = Rm + (size_t)(s - 1) * N, *lin = Lm + (size_t)s * N;
-                __half2 *lout = Lm + (size_t)(s - 1) * N;
+                const int rin = RO + (s - 1) * N + j, lin = s * N + j, lout = (s - 1) * N + j;
                 __half2 ru0, ru1, rl0, rl1, lu0, lu1, ll0, ll1;
                 if (s == n - 1) { lu0 = ch_up[0]; lu1 = ch_up[1]; ll0 = ch_lo[0]; ll1 = ch_lo[1]; }
-                else { ld2h(lin + j, lu0, lu1); ld2h(lin + j + d, ll0, ll1); }
-                ld2h(rin + j, ru0, ru1);
-                ld2h(rin + j + d, rl0, rl1);
+                else { LD(lin, lu0, lu1); LD(lin + d, ll0, ll1); }
+                LD(rin, ru0, ru1);
+                LD(rin + d, rl0, rl1);
                 const __half2 ou0 = chk_h2(lu0, __hadd2(ll0, rl0)), ou1 = chk_h2(lu1, __hadd2(ll1, rl1));
                 const __half2 ol0 = __hadd2(ll0, chk_h2(ru0, lu0)), ol1 = __hadd2(ll1, chk_h2(ru1, lu1));
                 if (a.early_stop) {
                     __half2 pu0, pu1, pl0, pl1;
-                    ld2h(lout + j, pu0, pu1);
-                    ld2h(lout + j + d, pl0, pl1);
+                    LD(lout, pu0, pu1);
+                    LD(lout + d, pl0, pl1);
                     changed |= (int)((bits_of(ou0) ^ bits_of(pu0)) | (bits_of(ou1) ^ bits_of(pu1)) | (bits_of(ol0) ^ bits_of(pl0)) | (bits_of(ol1) ^ bits_of(pl1))) != 0;
                 }
-                st2h(lout + j, ou0, ou1);
-                st2h(lout + j + d, ol0, ol1);
+                ST(lout, ou0, ou1);
+                ST(lout + d, ol0, ol1);
                 cta_sync_h2<THREADS>();
             }
             sweeps = it + 1;
