@@ -334,7 +334,9 @@ __global__ void __launch_bounds__(32, (sizeof(real) == 4) ? 32 : 24) list_decode
             const uint32_t fmask = LMASK << fbase;
             const uint32_t both = m0 & m1 & fmask, dead = ~(m0 | m1) & fmask;
             int src = lane;
-            if (__any_sync(0xffffffffu, !(k0 || k1))) {
+            real pc1 = c1;
+            if (__any_sync(0xffffffffu, !(k0 || k1))) {  // some slot of the warp is free: paths may move (otherwise every path
+                                                          // keeps exactly one child in place and nothing is exchanged)
                 // t-th free slot (ascending) takes the bit-1 branch of the t-th both-survivor (ascending): SCL_1024.c:636-660.
                 // The both-survivors publish their lane at their rank; the free slots read the entry of their own rank.
                 const uint32_t below = (1u << lane) - 1u;
@@ -342,21 +344,21 @@ __global__ void __launch_bounds__(32, (sizeof(real) == 4) ? 32 : 24) list_decode
                 __syncwarp();
                 if (!(k0 || k1) && __popc(dead & below) < __popc(both)) src = (int)sm_slot[fbase + __popc(dead & below)];
                 __syncwarp();
-            }
-            const real pc1 = __shfl_sync(0xffffffffu, c1, src);
-            if (keep2) {  // stage 2 is read again by the g step before leaf 2 only
+                pc1 = __shfl_sync(0xffffffffu, c1, src);
+                if (keep2) {  // stage 2 is read again by the g step before leaf 2 only
 #pragma unroll
-                for (int e = 0; e < 4; e++) s2[e] = __shfl_sync(0xffffffffu, s2[e], src);
+                    for (int e = 0; e < 4; e++) s2[e] = __shfl_sync(0xffffffffu, s2[e], src);
+                }
+                if (first) {  // stage 1 is read by the g step of the odd leaf that follows
+                    s1[0] = __shfl_sync(0xffffffffu, s1[0], src);
+                    s1[1] = __shfl_sync(0xffffffffu, s1[1], src);
+                }
+                ptr = __shfl_sync(0xffffffffu, ptr, src);
+                bptr = __shfl_sync(0xffffffffu, bptr, src);
+                Blow = __shfl_sync(0xffffffffu, Blow, src);
+                B5 = __shfl_sync(0xffffffffu, B5, src);
+                ug = __shfl_sync(0xffffffffu, ug, src);
             }
-            if (first) {  // stage 1 is read by the g step of the odd leaf that follows
-                s1[0] = __shfl_sync(0xffffffffu, s1[0], src);
-                s1[1] = __shfl_sync(0xffffffffu, s1[1], src);
-            }
-            ptr = __shfl_sync(0xffffffffu, ptr, src);
-            bptr = __shfl_sync(0xffffffffu, bptr, src);
-            Blow = __shfl_sync(0xffffffffu, Blow, src);
-            B5 = __shfl_sync(0xffffffffu, B5, src);
-            ug = __shfl_sync(0xffffffffu, ug, src);
             uint32_t u;
             if (src != lane) { pm = pc1; u = 1u; }
             else if (k0) { pm = c0; u = 0u; }
