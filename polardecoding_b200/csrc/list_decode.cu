@@ -487,6 +487,24 @@ __global__ void __launch_bounds__(32, (sizeof(real) == 4) ? 32 : 24) list_decode
             }
             ug = 0;
             const uint32_t inib = a.m.info[j4 >> 3] >> ((j4 & 7) * 4);  // which of the four leaves carry information
+            if (L > 1 && (inib & 0xFu) == 0u) {
+                // four frozen leaves (every decision 0): the two in-register levels are a fixed butterfly, so the four leaf LLRs and
+                // their table look-ups are independent; only the four path-metric additions keep the leaf order (SCL_1024.c:489-500)
+                const real f0 = chk_lean<real>(s2[0], s2[2]), f1 = chk_lean<real>(s2[1], s2[3]);
+                const real g0 = s2[2] + s2[0], g1 = s2[3] + s2[1];
+                const real lam[4] = {chk_lean<real>(f0, f1), f1 + f0, chk_lean<real>(g0, g1), g1 + g0};
+                real pen[4];
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const real ab = rabs(lam[e]);
+                    const real t = tbl8<real>(ab);
+                    real tp = t;
+                    tp += ab;
+                    pen[e] = (lam[e] < (real)0) ? tp : t;
+                }
+#pragma unroll
+                for (int e = 0; e < 4; e++) pm = pm + pen[e];
+            } else
 #pragma unroll 1
             for (int p = 0; p < 2; p++) {
                 if (p == 0) {  // f at stage 1
