@@ -1,6 +1,10 @@
 // Internal (C++) interface between the C-ABI layer (api.cu) and the kernel translation units.
 #pragma once
+#ifdef POLAR_EMU  // CPU warp emulator, test infrastructure only (tests/emu)
+#include "cuda_emu.h"
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 namespace polar {

@@ -147,7 +147,11 @@ __global__ void __launch_bounds__(32, (sizeof(real) == 4) ? 32 : 24) list_decode
     constexpr uint32_t LMASK = (L == 32) ? 0xffffffffu : ((1u << (L & 31)) - 1u);  // lanes of one frame
     const real INF = RT::inf();
 
+#ifdef POLAR_EMU
+    unsigned char *const smem_raw = emu::g.smem;
+#else
     extern __shared__ __align__(16) unsigned char smem_raw[];
+#endif
     V4 *const sm_stage = reinterpret_cast<V4 *>(smem_raw);  // stage s (3<=s<TOP): group i4 of lane pl at [8*(2^s-8) + i4*32 + pl]
     uint32_t *const sm_bits = reinterpret_cast<uint32_t *>(smem_raw + (size_t)C::SM_STAGE_REALS * sizeof(real));
     uint32_t *const sm_slot = sm_bits + C::SM_BIT_WORDS;  // [32]: lane id of the t-th both-survivor of each frame
@@ -632,16 +636,25 @@ __global__ void __launch_bounds__(32, (sizeof(real) == 4) ? 32 : 24) list_decode
 }
 
 // ---------------------------------------------------------------- dispatch
-template <typename real, int LOGN, int L>
-struct ListDispatch {
 #ifndef POLAR_SMEM_TOP
 #define POLAR_SMEM_TOP 5
 #endif
 #ifndef POLAR_BITS_TOP
 #define POLAR_BITS_TOP 7
 #endif
-    static constexpr int SMEM_TOP = POLAR_SMEM_TOP, BITS_TOP = POLAR_BITS_TOP;
+// which kernel configuration serves (real, N, L); shared by the launcher below and by the CPU emulator tests
+template <typename real, int LOGN, int L>
+struct ListDispatchCfg {
+    static constexpr int SMEM_TOP = POLAR_SMEM_TOP, BITS_TOP = POLAR_BITS_TOP, THREADS = 32;
     using C = ListCfg<real, LOGN, L, SMEM_TOP, BITS_TOP>;
+};
+
+#ifndef POLAR_EMU
+template <typename real, int LOGN, int L>
+struct ListDispatch {
+    using D = ListDispatchCfg<real, LOGN, L>;
+    static constexpr int SMEM_TOP = D::SMEM_TOP, BITS_TOP = D::BITS_TOP;
+    using C = typename D::C;
     static cudaError_t plan(ListPlan *p)
     {
         auto kern = list_decode_kernel<real, LOGN, L, SMEM_TOP, BITS_TOP>;
@@ -692,5 +705,6 @@ cudaError_t launch_list(const ListArgs &a, int n, int L, bool f64, int grid, cud
 #undef X
     return cudaErrorInvalidValue;
 }
+#endif  // !POLAR_EMU
 
 }  // namespace polar

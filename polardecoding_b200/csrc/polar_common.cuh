@@ -7,7 +7,11 @@
 //   chk<real>  : CHK(),  /root/reference/SC_128.c:284-315
 //   phi_tbl    : table part of PHI(), /root/reference/SCL_1024.c:481-502 (same 8-level table)
 #pragma once
+#ifdef POLAR_EMU  // CPU warp emulator, test infrastructure only (tests/emu)
+#include "cuda_emu.h"
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 namespace polar {
@@ -103,12 +107,50 @@ __device__ __forceinline__ real chk(real a, real b)
 // slots, bit-identical results.  FFMA2 costs ~2.5 FFMA pipe slots (tools/ubench/chk_variants.cu, V7), so this only pays
 // where the issue rate, not the FMA pipe, is the limit: the list decoder gains 5 %, BP (FMA-pipe heavy) loses 2 % -- so
 // list_decode.cu uses chk_lean, bp_decode.cu uses chk_mix_f32 with two packed steps (below).
+#ifndef POLAR_EMU
 __device__ __forceinline__ unsigned long long pk2(float lo, float hi)
 {
     unsigned long long r;
     asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
     return r;
 }
+__device__ __forceinline__ void unpk2(unsigned long long v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b)
+{
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c)
+{
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ float step_alu(float x, float t)
+{
+    float r;
+    asm("set.lt.f32.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(t));
+    return r;
+}
+#else  // the same operations, element by element, for the CPU warp emulator (IEEE single, one rounding per fma)
+__device__ __forceinline__ unsigned long long pk2(float lo, float hi) { return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32); }
+__device__ __forceinline__ void unpk2(unsigned long long v, float &lo, float &hi) { lo = __uint_as_float((unsigned)v); hi = __uint_as_float((unsigned)(v >> 32)); }
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b)
+{
+    float al, ah, bl, bh;
+    unpk2(a, al, ah); unpk2(b, bl, bh);
+    volatile float l = al * bl, h = ah * bh;
+    return pk2(l, h);
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c)
+{
+    float al, ah, bl, bh, cl, ch;
+    unpk2(a, al, ah); unpk2(b, bl, bh); unpk2(c, cl, ch);
+    return pk2(fmaf(al, bl, cl), fmaf(ah, bh, ch));
+}
+__device__ __forceinline__ float step_alu(float x, float t) { return (x < t) ? 1.0f : 0.0f; }
+#endif
 template <typename real>
 __device__ __forceinline__ real chk_lean(real a, real b) { return chk<real>(a, b); }
 template <>
@@ -118,15 +160,15 @@ __device__ __forceinline__ float chk_lean<float>(float a, float b)
     const float s = fabsf(a + b), d = fabsf(a - b);
     unsigned long long acc, t;
 #define POLAR_ST(x, T) __saturatef(fmaf(x, NB, T * B))
-#define POLAR_STEP(T, H) t = pk2(POLAR_ST(s, T), POLAR_ST(d, T)); asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(t), "l"(pk2(__int_as_float(H), __int_as_float(H))));
+#define POLAR_STEP(T, H) acc = fma2(pk2(POLAR_ST(s, T), POLAR_ST(d, T)), pk2(__int_as_float(H), __int_as_float(H)), acc);
     t = pk2(POLAR_ST(s, 4.5f), POLAR_ST(d, 4.5f));
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(acc) : "l"(t), "l"(pk2(__int_as_float(0x3d4ccccd), __int_as_float(0x3d4ccccd))));
+    acc = mul2(t, pk2(__int_as_float(0x3d4ccccd), __int_as_float(0x3d4ccccd)));
     POLAR_STEP(2.252f, 0x3dccccce) POLAR_STEP(1.508f, 0x3dcccccc) POLAR_STEP(1.05f, 0x3dcccccc)
     POLAR_STEP(0.71f, 0x3dcccccc) POLAR_STEP(0.433f, 0x3dccccd0) POLAR_STEP(0.196f, 0x3dccccc8)
 #undef POLAR_STEP
 #undef POLAR_ST
     float ts, td;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(ts), "=f"(td) : "l"(acc));
+    unpk2(acc, ts, td);
     const float m = fminf(fabsf(a), fabsf(b));
     return real_traits<float>::xsign(m, a, b) + (ts - td);
 }
@@ -135,12 +177,6 @@ __device__ __forceinline__ float chk_lean<float>(float a, float b)
 // the indicator [x < t] comes either from the FMA pipe (FFMA.SAT, as above) or from the ALU pipe (FSET.BF, the first KM steps),
 // and the two sums accumulate packed (one FFMA2 for both, the first KP steps) or scalar.  Every choice gives exactly 1.0f/0.0f
 // indicators and the same accumulation order, so the results are bit-identical for all (KP, KM).
-__device__ __forceinline__ float step_alu(float x, float t)
-{
-    float r;
-    asm("set.lt.f32.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(t));
-    return r;
-}
 template <int KP, int KM>
 __device__ __forceinline__ float chk_mix_f32(float a, float b)
 {
@@ -159,12 +195,11 @@ __device__ __forceinline__ float chk_mix_f32(float a, float b)
         ts = hs[0] * __int_as_float(H[0]);
         td = hd[0] * __int_as_float(H[0]);
     } else {
-        unsigned long long acc;
-        asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(acc) : "l"(pk2(hs[0], hd[0])), "l"(pk2(__int_as_float(H[0]), __int_as_float(H[0]))));
+        unsigned long long acc = mul2(pk2(hs[0], hd[0]), pk2(__int_as_float(H[0]), __int_as_float(H[0])));
 #pragma unroll
         for (int k = 1; k < 7; k++)
-            if (k < KP) asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(pk2(hs[k], hd[k])), "l"(pk2(__int_as_float(H[k]), __int_as_float(H[k]))));
-        asm("mov.b64 {%0, %1}, %2;" : "=f"(ts), "=f"(td) : "l"(acc));
+            if (k < KP) acc = fma2(pk2(hs[k], hd[k]), pk2(__int_as_float(H[k]), __int_as_float(H[k])), acc);
+        unpk2(acc, ts, td);
     }
 #pragma unroll
     for (int k = 1; k < 7; k++)
