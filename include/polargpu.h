@@ -61,7 +61,7 @@ typedef struct pg_params {
     int crc_systematic;    /* 0: w = v*g (CASCL_1024_L8.c:251-266); 1: parity-first systematic (CASCL_1024_sys.c:776-789) */
     int decoder;           /* enum pg_decoder */
     int list_size;         /* L: 1 (SC) or 2,4,8,16,32 */
-    int iter_max;          /* BP sweeps: 100 (BP_1024.c:16); ignored otherwise */
+    int iter_max;          /* BP sweeps: 100 (BP_1024.c:16), 1..255 (the per-frame word holds the executed sweeps in 8 bits); ignored otherwise */
     int bp_early_stop;     /* bit 0: stop a frame once a sweep leaves every message bit-identical (decisions unchanged, parity-safe);
                               bit 1: also stop when the hard decisions form a codeword (u G = x, "G-matrix" rule; not in the
                               reference, FER-level equivalence only; not available with PG_REAL_H2) */
@@ -111,8 +111,18 @@ int pg_decode_llr_packed(pg_ctx *ctx, const void *llr, int llr_is_f64, size_t B,
  * NULL.  With pg_bpr_config active and a BP context this also accumulates the BPR statistic. */
 int pg_decode_llr_counted(pg_ctx *ctx, const void *llr, int llr_is_f64, size_t B, const uint8_t *u_true, uint8_t *u_hat,
                           pg_counters *acc, uint16_t *frame_err);
-/* same with DEVICE pointers and packed output (u_hat_packed: [B][N/32] words); no copies, asynchronous on the ctx stream */
-int pg_decode_llr_device(pg_ctx *ctx, const void *d_llr, int llr_is_f64, size_t B, uint32_t *d_u_hat_packed, uint32_t *d_flags);
+/* same with DEVICE pointers and packed output (u_hat_packed: [B][N/32] words); no copies, asynchronous on the ctx stream.
+ * d_frame_info ([B], DEVICE, may be NULL) receives the kernels' RAW per-frame word (layout: PG_INFO_* below), not the
+ * host calls' compact `flags`: the call launches nothing but the decode kernel.  PG_INFO_TO_FLAGS(w) converts one word. */
+int pg_decode_llr_device(pg_ctx *ctx, const void *d_llr, int llr_is_f64, size_t B, uint32_t *d_u_hat_packed, uint32_t *d_frame_info);
+
+/* per-frame word written by the decode kernels (d_frame_info of the *_device calls, frame_info of pg_truncate_info) */
+#define PG_INFO_ERRBITS_MASK 0xFFFFu      /* bits 0..15: wrong counted bits (only when a truth vector was supplied), saturating */
+#define PG_INFO_TIE (1u << 16)            /* list decoders: exact PM tie across the list boundary in this frame */
+#define PG_INFO_CRC_FAIL (1u << 17)       /* CA-SCL: no path passed the CRC */
+#define PG_INFO_SWEEPS_SHIFT 24           /* bits 24..31: BP sweeps executed (iter_max <= 255) */
+/* the compact `flags` word of pg_decode_llr / pg_decode_llr_packed: bit0 tie, bit1 no CRC pass, bits 8..15 BP sweeps */
+#define PG_INFO_TO_FLAGS(w) ((((w) >> 16) & 3u) | (((w) >> PG_INFO_SWEEPS_SHIFT) << 8))
 
 /* device-resident variant with the on-device error count: d_truth_packed ([B][N/32], e.g. from pg_channel_device) is
  * compared on the counted positions; block/bit errors, tie and CRC-fail frames are ADDED to the context's device

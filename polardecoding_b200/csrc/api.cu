@@ -51,6 +51,9 @@ NcclApi g_nccl;
 
 int ilog2(int v) { int k = 0; while ((1 << k) < v) k++; return k; }
 
+// the public PG_INFO_* layout (include/polargpu.h) is the kernels' frame-info word (engine.h)
+static_assert(PG_INFO_TIE == polar::kInfoTie && PG_INFO_CRC_FAIL == polar::kInfoCrcFail, "frame-info layout");
+
 }  // namespace
 
 constexpr int kPipeLanes = 4, kPipeBufs = 2 * kPipeLanes;
@@ -88,6 +91,7 @@ struct pg_ctx {
     void *d_scratch = nullptr;
     int grid = 0;
     size_t scratch_per_cta = 0;
+    size_t frames_per_cta = 1;  // frames one CTA of the decode kernel holds at a time
     // pipelined host path (pg_decode_llr*): a copy stream feeds two buffer sets per lane; the list decoders run kPipeLanes
     // quarter-grid kernels side by side on as many compute streams (their phases interleave instead of marching in lockstep),
     // BP runs one
@@ -227,7 +231,7 @@ extern "C" int pg_create(const pg_params *p, pg_ctx **out)
     if (p->decoder != PG_DEC_BP && (L < 1 || L > 32 || (L & (L - 1)))) return fail(PG_ERR_ARG, "list_size must be 1,2,4,8,16,32");
     if ((p->decoder == PG_DEC_SCL || p->decoder == PG_DEC_CASCL) && L < 2) return fail(PG_ERR_ARG, "list decoders need list_size >= 2");
     if (p->decoder == PG_DEC_CASCL && p->crc_bits == 0) return fail(PG_ERR_ARG, "CA-SCL needs a CRC");
-    if (p->decoder == PG_DEC_BP && (p->iter_max < 1 || p->N < 64)) return fail(PG_ERR_ARG, "BP needs iter_max >= 1 and N >= 64");
+    if (p->decoder == PG_DEC_BP && (p->iter_max < 1 || p->iter_max > 255 || p->N < 64)) return fail(PG_ERR_ARG, "BP needs 1 <= iter_max <= 255 and N >= 64");
 
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -296,22 +300,25 @@ extern "C" int pg_create(const pg_params *p, pg_ctx **out)
         if (pe != cudaSuccess) { ctx->err = std::string("no BP kernel for this N: ") + cudaGetErrorString(pe); return bail(PG_ERR_UNSUPPORTED); }
         if (bp.ctas_per_sm < 1) { ctx->err = "BP kernel does not fit on an SM"; return bail(PG_ERR_UNSUPPORTED); }
         ctx->grid = ctx->sm_count * bp.ctas_per_sm;
+        ctx->frames_per_cta = ctx->h2 ? 2 : 1;
     } else {
         ListPlan lp;
         cudaError_t pe = list_plan(ctx->n, L, ctx->f64, &lp);
         if (pe != cudaSuccess) { ctx->err = std::string("no list kernel for this (N, L): ") + cudaGetErrorString(pe); return bail(PG_ERR_UNSUPPORTED); }
         if (lp.ctas_per_sm < 1) { ctx->err = "list kernel does not fit on an SM"; return bail(PG_ERR_UNSUPPORTED); }
         int per_sm = lp.ctas_per_sm;
+        if (getenv("POLARGPU_DEBUG_PLAN")) fprintf(stderr, "polargpu: list kernel plan: %d CTAs/SM, %d frames/CTA, %zu B smem/CTA, %zu B scratch/CTA\n", lp.ctas_per_sm, lp.frames_per_cta, lp.smem, lp.scratch_per_cta);
         if (const char *cap = getenv("POLARGPU_LIST_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(cap)));  // tuning aid
         ctx->grid = ctx->sm_count * per_sm;
         ctx->scratch_per_cta = lp.scratch_per_cta;
+        ctx->frames_per_cta = (size_t)lp.frames_per_cta;
         if (lp.scratch_per_cta) CUC(cudaMalloc(&ctx->d_scratch, lp.scratch_per_cta * (size_t)ctx->grid));
     }
     {
         // frames per launch: about 2^27 LLRs, rounded to whole waves of the decode kernel so that no SM idles at the end of a launch
         const char *env = getenv("POLARGPU_CHUNK");
         size_t c = env ? (size_t)atoll(env) : ((size_t)1 << 27) / (size_t)p->N;
-        const size_t wave = (size_t)ctx->grid * ((p->decoder == PG_DEC_BP) ? (ctx->h2 ? 2 : 1) : (size_t)(32 / L));
+        const size_t wave = (size_t)ctx->grid * ctx->frames_per_cta;
         if (!env && wave > 0) c = std::max<size_t>(1, c / wave) * wave;
         ctx->chunk_max = std::max<size_t>(c, 32);
     }
@@ -436,9 +443,8 @@ static int run_decode_on(pg_ctx *ctx, cudaStream_t st, int grid_cap, int cta_off
             a.coop_groups = getenv("POLARGPU_NO_COOP") ? 0 : first / 4;
         }
         a.m = ctx->masks;
-        const size_t fpw = 32 / (size_t)p.list_size;
-        const size_t groups = (B + fpw - 1) / fpw;
-        const int grid = (int)std::min<size_t>((size_t)grid_cap, groups);
+        const size_t ctas = (B + ctx->frames_per_cta - 1) / ctx->frames_per_cta;
+        const int grid = (int)std::min<size_t>((size_t)grid_cap, ctas);
         CU(launch_list(a, ctx->n, p.list_size, ctx->f64, std::max(grid, 1), st));
     }
     if (timed) {
@@ -454,7 +460,7 @@ static int run_decode(pg_ctx *ctx, const void *d_llr, size_t B, const uint32_t *
     return run_decode_on(ctx, ctx->st, ctx->grid, 0, d_llr, B, d_truth, d_uhat, d_info, count);
 }
 
-extern "C" int pg_decode_llr_device(pg_ctx *ctx, const void *d_llr, int llr_is_f64, size_t B, uint32_t *d_u_hat_packed, uint32_t *d_flags)
+extern "C" int pg_decode_llr_device(pg_ctx *ctx, const void *d_llr, int llr_is_f64, size_t B, uint32_t *d_u_hat_packed, uint32_t *d_frame_info)
 {
     if (!ctx || !d_llr) return PG_ERR_ARG;
     if (B == 0) return PG_OK;
@@ -467,7 +473,7 @@ extern "C" int pg_decode_llr_device(pg_ctx *ctx, const void *d_llr, int llr_is_f
         ctx->launches++;
         src = ctx->d_llr;
     }
-    return run_decode(ctx, src, B, nullptr, d_u_hat_packed, d_flags, false);
+    return run_decode(ctx, src, B, nullptr, d_u_hat_packed, d_frame_info, false);
 }
 
 extern "C" int pg_decode_count_device(pg_ctx *ctx, const void *d_llr, int llr_is_f64, size_t B, const uint32_t *d_truth_packed,
@@ -501,8 +507,7 @@ extern "C" int pg_channel_device(pg_ctx *ctx, double ebn0_db, uint64_t first_fra
 
 static uint64_t wave_frames(const pg_ctx *ctx)
 {
-    const uint64_t per_cta = (ctx->p.decoder == PG_DEC_BP) ? (ctx->h2 ? 2 : 1) : (uint64_t)(32 / ctx->p.list_size);
-    return (uint64_t)ctx->grid * per_cta;
+    return (uint64_t)ctx->grid * ctx->frames_per_cta;
 }
 
 // Host-pointer decode.  Batches larger than one wave of the decode kernel are cut into wave-sized chunks and pipelined over
@@ -574,7 +579,7 @@ static int decode_host(pg_ctx *ctx, const void *llr, int llr_is_f64, size_t B, u
         }
     }
     if (flags)
-        for (size_t i = 0; i < B; i++) flags[i] = ((flags[i] >> 16) & 3u) | ((flags[i] >> 24) << 8);
+        for (size_t i = 0; i < B; i++) flags[i] = PG_INFO_TO_FLAGS(flags[i]);
     return PG_OK;
 }
 

@@ -38,6 +38,9 @@
 //    rule would have been ambiguous ("Oops!", SCL_1024.c:621).
 #include "engine.h"
 #include "polar_common.cuh"
+#ifndef POLAR_EMU
+#include <algorithm>
+#endif
 
 namespace polar {
 
@@ -46,22 +49,34 @@ template <typename real> struct alignas(16) vec4 { real v[4]; };
 template <int L> struct ptr_word { using type = uint32_t; static constexpr int W = 4; };
 template <> struct ptr_word<32> { using type = unsigned long long; static constexpr int W = 5; };
 
-template <typename real, int LOGN, int L, int SMEM_TOP, int BITS_TOP>
+// TMH > TML: the LLR stages TML..TMH-1 live in TENSOR MEMORY (sm_100a: 128 lanes x 512 columns of 32 bits per SM, idle in a
+// kernel without tensor-core work): a warp owns the 32 TMEM lanes of its quarter, lane = path as everywhere else, column = index
+// within the stages.  CTAs then hold four independent warps (one per TMEM lane quarter) and allocate the columns once.
+// Stages 3..TML-1 are shared memory, TMH.. the global scratch.
+template <typename real, int LOGN, int L, int SMEM_TOP, int BITS_TOP, int TML = 0, int TMH = 0>
 struct ListCfg {
     static constexpr int N = 1 << LOGN;
     static constexpr int W = (N + 31) / 32;
     static constexpr int FPW = 32 / L;
-    static constexpr int TOP = (SMEM_TOP < LOGN) ? SMEM_TOP : LOGN;            // LLR stages 2..TOP-1 in smem
+    static constexpr bool HAS_TM = TMH > TML;
+    static_assert(!HAS_TM || (TML >= 3 && TMH <= LOGN - 1), "tensor-memory stages: above stage 2, the first scratch stage below the channel");
+    static constexpr int TOP = HAS_TM ? TML : ((SMEM_TOP < LOGN) ? SMEM_TOP : LOGN);  // LLR stages 3..TOP-1 in smem
+    static constexpr int GLO = HAS_TM ? TMH : TOP;                             // first LLR stage in the global scratch
+    static constexpr int WARPS = HAS_TM ? 4 : 1;                               // warps per CTA (independent of each other)
+    static constexpr int THREADS = 32 * WARPS;
+    static constexpr int TM_USED = HAS_TM ? ((1 << TMH) - (1 << TML)) * (int)(sizeof(real) / 4) : 0;
+    static constexpr int TM_COLS = !HAS_TM ? 0 : (TM_USED <= 32 ? 32 : TM_USED <= 64 ? 64 : TM_USED <= 128 ? 128 : TM_USED <= 256 ? 256 : 512);
+    static_assert(TM_USED <= 512, "tensor-memory allocation: at most 512 columns");
     static constexpr int BTOP = (BITS_TOP < LOGN + 1) ? BITS_TOP : LOGN + 1;    // bit stages 6..BTOP-1 in smem
     static constexpr int BLO = (BTOP > 6) ? BTOP : 6;                           // first bit stage in global scratch
     static constexpr int SM_STAGE_REALS = 32 * ((1 << TOP) - 8);          // stages 3..TOP-1 (stage 2 lives in registers only)
-    static_assert(SMEM_TOP >= 4, "stage 3 is always in shared memory");
     static constexpr int SM_BIT_WORDS = (BTOP > 6) ? 32 * ((1 << (BTOP - 5)) - 2) : 0;
     static constexpr int SM_SLOT_WORDS = (L > 1) ? 32 : 0;                      // clone-source table, one word per lane
-    static constexpr size_t SMEM = (size_t)SM_STAGE_REALS * sizeof(real) + (size_t)SM_BIT_WORDS * 4 + (size_t)SM_SLOT_WORDS * 4;
-    static constexpr size_t GS_REALS = 32 * (size_t)((1 << LOGN) - (1 << TOP));                    // stages TOP..LOGN-1
+    static constexpr size_t SMEM = (size_t)SM_STAGE_REALS * sizeof(real) + (size_t)SM_BIT_WORDS * 4 + (size_t)SM_SLOT_WORDS * 4;  // per warp
+    static constexpr size_t SMEM_CTA = SMEM * WARPS + (HAS_TM ? 16 : 0);       // + the word tcgen05.alloc writes
+    static constexpr size_t GS_REALS = 32 * (size_t)((1 << LOGN) - (1 << GLO));                    // stages GLO..LOGN-1
     static constexpr size_t GS_BIT_WORDS = (LOGN >= BLO) ? 32 * (size_t)((1 << (LOGN - 4)) - (1 << (BLO - 5))) : 0;  // BLO..LOGN
-    static constexpr size_t GS_BYTES = GS_REALS * sizeof(real) + GS_BIT_WORDS * 4;
+    static constexpr size_t GS_BYTES = GS_REALS * sizeof(real) + GS_BIT_WORDS * 4;                 // per warp
 };
 
 // explicit 128-bit accesses (the compiler otherwise splits some of these into scalar loads)
@@ -88,6 +103,102 @@ __device__ __forceinline__ void stv(vec4<double> *p, const vec4<double> &o)
 }
 __device__ __forceinline__ float rmax(float a, float b) { return fmaxf(a, b); }
 __device__ __forceinline__ double rmax(double a, double b) { return fmax(a, b); }
+
+// ---- tensor memory: one V4 (four reals of one path) = 4 (float) or 8 (double) consecutive columns of the lane's TMEM row.
+// tcgen05.ld / tcgen05.st are asynchronous: tm_wait_ld() before the loaded registers are read, tm_wait_st() before the stored
+// columns are loaded again.  `tm` = allocation base + (32 * (warp % 4)) << 16; `v4` = index of the V4 within the stage.
+#ifdef POLAR_EMU
+__device__ __forceinline__ uint32_t tm_alloc(uint32_t *slot, int cols, int warp) { if (warp == 0 && emu::lane_id() == 0) *slot = emu::tmem_alloc((uint32_t)cols); return *slot; }
+__device__ __forceinline__ void tm_free(uint32_t, int) {}
+__device__ __forceinline__ void tm_wait_ld() {}
+__device__ __forceinline__ void tm_wait_st() {}
+template <typename real> __device__ __forceinline__ vec4<real> tm_ld(uint32_t tm, int v4)
+{
+    vec4<real> o;
+    constexpr int C = (int)(sizeof(vec4<real>) / 4);
+    uint32_t w[C];
+    for (int e = 0; e < C; e++) w[e] = *emu::tmem_cell(tm + (uint32_t)(v4 * C), e);
+    memcpy(&o, w, sizeof(o));
+    return o;
+}
+template <typename real> __device__ __forceinline__ void tm_st(uint32_t tm, int v4, const vec4<real> &o)
+{
+    constexpr int C = (int)(sizeof(vec4<real>) / 4);
+    uint32_t w[C];
+    memcpy(w, &o, sizeof(o));
+    for (int e = 0; e < C; e++) *emu::tmem_cell(tm + (uint32_t)(v4 * C), e) = w[e];
+}
+#else
+__device__ __forceinline__ uint32_t tm_alloc(uint32_t *slot, int cols, int warp)  // all threads of the CTA call this
+{
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(slot)), "r"(cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    return *reinterpret_cast<volatile uint32_t *>(slot);
+}
+__device__ __forceinline__ void tm_free(uint32_t base, int cols)  // warp 0, after a __syncthreads()
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tm_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+template <typename real> __device__ __forceinline__ vec4<real> tm_ld(uint32_t tm, int v4);
+template <> __device__ __forceinline__ vec4<float> tm_ld<float>(uint32_t tm, int v4)
+{
+    uint32_t a, b, c, d;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(tm + (uint32_t)(v4 * 4)) : "memory");
+    vec4<float> o;
+    o.v[0] = __uint_as_float(a); o.v[1] = __uint_as_float(b); o.v[2] = __uint_as_float(c); o.v[3] = __uint_as_float(d);
+    return o;
+}
+template <> __device__ __forceinline__ vec4<double> tm_ld<double>(uint32_t tm, int v4)
+{
+    uint32_t w[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "r"(tm + (uint32_t)(v4 * 8)) : "memory");
+    vec4<double> o;
+#pragma unroll
+    for (int e = 0; e < 4; e++) o.v[e] = __hiloint2double((int)w[2 * e + 1], (int)w[2 * e]);
+    return o;
+}
+__device__ __forceinline__ void tm_st(uint32_t tm, int v4, const vec4<float> &o)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(tm + (uint32_t)(v4 * 4)), "r"(__float_as_uint(o.v[0])),
+                 "r"(__float_as_uint(o.v[1])), "r"(__float_as_uint(o.v[2])), "r"(__float_as_uint(o.v[3])) : "memory");
+}
+__device__ __forceinline__ void tm_st(uint32_t tm, int v4, const vec4<double> &o)
+{
+    uint32_t w[8];
+#pragma unroll
+    for (int e = 0; e < 4; e++) { w[2 * e] = (uint32_t)__double2loint(o.v[e]); w[2 * e + 1] = (uint32_t)__double2hiint(o.v[e]); }
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(tm + (uint32_t)(v4 * 8)), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+                 "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+}
+#endif
+// L1 prefetch of one 16-byte element per lane (no register, no scoreboard)
+__device__ __forceinline__ void prefetch_l1(const void *p)
+{
+#ifndef POLAR_EMU
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+#ifndef POLAR_PF_MAX
+#define POLAR_PF_MAX 0   // g-layers up to this stage get their source prefetched into the L1 one leaf group ahead (0: off)
+#endif
+// a V4 as seen by lane `src` (clone-pointer indirection for tensor memory, where a lane reaches its own row only)
+template <typename real> __device__ __forceinline__ vec4<real> shfl_v4(const vec4<real> &v, int src)
+{
+    vec4<real> o;
+#pragma unroll
+    for (int e = 0; e < 4; e++) o.v[e] = __shfl_sync(0xffffffffu, v.v[e], src);
+    return o;
+}
 
 // lo <- max of lo, hi <- min of hi over the L lanes of a frame (mask = those lanes).  Path metrics are non-negative (or +inf), so
 // in fp32 their bit patterns order like unsigned integers and one REDUX per value replaces log2(L) shuffle + min/max steps.
@@ -116,6 +227,10 @@ __device__ __forceinline__ void frame_minmax(double &lo, double &hi, uint32_t)
 }
 
 // one CHK / g evaluation of four neighbouring nodes
+// (Inline on purpose.  As a called function the four-CHK block costs eight argument moves and spills around every call:
+// 13.4 -> 11.5 M frames/s.  What matters instead is the NUMBER of inline copies: the warps of an SM sit at unrelated program
+// counters, and 98 KB of SASS instead of 68 KB raised stall_no_instruction from 8 % to 44 % of the samples -- so every f-layer
+// of the hot loop goes through ONE loop body whose loads and stores switch on warp-uniform flags.)
 template <typename real>
 __device__ __forceinline__ vec4<real> f4(const vec4<real> &x, const vec4<real> &y)
 {
@@ -133,33 +248,45 @@ __device__ __forceinline__ vec4<real> g4(const vec4<real> &up, const vec4<real> 
     return o;
 }
 
-template <typename real, int LOGN, int L, int SMEM_TOP, int BITS_TOP>
-__global__ void __launch_bounds__(32, (sizeof(real) == 4) ? 32 : 24) list_decode_kernel(const ListArgs a)
+template <typename real, int LOGN, int L, int SMEM_TOP, int BITS_TOP, int TML, int TMH>
+__global__ void __launch_bounds__(ListCfg<real, LOGN, L, SMEM_TOP, BITS_TOP, TML, TMH>::THREADS,
+                                  (TMH > TML) ? ((TML > 3) ? 7 : 8) : ((sizeof(real) == 4) ? 32 : 24))
+list_decode_kernel(const ListArgs a)
 {
-    using C = ListCfg<real, LOGN, L, SMEM_TOP, BITS_TOP>;
+    using C = ListCfg<real, LOGN, L, SMEM_TOP, BITS_TOP, TML, TMH>;
     using RT = real_traits<real>;
     using PW = ptr_word<L>;
     using ptr_t = typename PW::type;
     using V4 = vec4<real>;
-    constexpr int N = C::N, W = C::W, FPW = C::FPW, TOP = C::TOP, BTOP = C::BTOP, BLO = C::BLO;
+    constexpr int N = C::N, W = C::W, FPW = C::FPW, TOP = C::TOP, BTOP = C::BTOP, BLO = C::BLO, GLO = C::GLO;
+    constexpr bool HAS_TM = C::HAS_TM;
     constexpr int PWID = PW::W;
     constexpr ptr_t PMASK = (ptr_t)((1u << PWID) - 1);
     constexpr uint32_t LMASK = (L == 32) ? 0xffffffffu : ((1u << (L & 31)) - 1u);  // lanes of one frame
     const real INF = RT::inf();
 
 #ifdef POLAR_EMU
-    unsigned char *const smem_raw = emu::g.smem;
+    unsigned char *const smem_cta = emu::g.smem;
 #else
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(16) unsigned char smem_cta[];
 #endif
+    // the warps of a CTA are independent decoders: each has its own shared-memory block, scratch block and TMEM lane quarter
+    const int wi = (C::WARPS > 1) ? (int)(threadIdx.x >> 5) : 0;
+    const unsigned gw = blockIdx.x * C::WARPS + wi, nwarps = gridDim.x * C::WARPS;
+    unsigned char *const smem_raw = smem_cta + (size_t)wi * C::SMEM;
     V4 *const sm_stage = reinterpret_cast<V4 *>(smem_raw);  // stage s (3<=s<TOP): group i4 of lane pl at [8*(2^s-8) + i4*32 + pl]
     uint32_t *const sm_bits = reinterpret_cast<uint32_t *>(smem_raw + (size_t)C::SM_STAGE_REALS * sizeof(real));
     uint32_t *const sm_slot = sm_bits + C::SM_BIT_WORDS;  // [32]: lane id of the t-th both-survivor of each frame
-    unsigned char *const gs_raw = reinterpret_cast<unsigned char *>(a.gscratch) + (size_t)blockIdx.x * C::GS_BYTES;
+    unsigned char *const gs_raw = reinterpret_cast<unsigned char *>(a.gscratch) + (size_t)gw * C::GS_BYTES;
     V4 *const gs_stage = reinterpret_cast<V4 *>(gs_raw);
     uint32_t *const gs_bits = reinterpret_cast<uint32_t *>(gs_raw + C::GS_REALS * sizeof(real));
+    uint32_t tm_base = 0, tm = 0;  // tensor memory: allocation of the CTA / this warp's lane quarter of it
+    if (HAS_TM) {
+        tm_base = tm_alloc(reinterpret_cast<uint32_t *>(smem_cta + C::SMEM * C::WARPS), C::TM_COLS, wi);
+        tm = tm_base + ((uint32_t)(wi & 3) << 21);  // lane field (bits 16..) = 32 * (warp % 4)
+    }
 
-    const int lane = threadIdx.x;
+    const int lane = (C::WARPS > 1) ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
     const int k = lane & (L - 1);
     const int fbase = lane - k;
     const int fl = lane / L;
@@ -169,15 +296,17 @@ __global__ void __launch_bounds__(32, (sizeof(real) == 4) ? 32 : 24) list_decode
     for (int i = 0; i * PWID < (int)(8 * sizeof(ptr_t)) - PWID + 1; i++) kpat |= (ptr_t)k << (i * PWID);
 
     // home arrays (generic pointers: one code path for shared and global stages keeps the hot loop small)
-    auto stage_at = [&](int s) -> V4 * {
-        return (s < TOP) ? (sm_stage + 8 * ((1 << s) - 8)) : (gs_stage + 8 * (size_t)((1 << s) - (1 << TOP)));
+    auto stage_at = [&](int s) -> V4 * {  // (never called for a tensor-memory stage)
+        return (s < TOP) ? (sm_stage + 8 * ((1 << s) - 8)) : (gs_stage + 8 * (size_t)((1 << s) - (1 << GLO)));
     };
+    auto in_tm = [&](int s) -> bool { return HAS_TM && s >= TML && s < TMH; };
+    auto tmoff = [&](int s) -> int { return ((1 << s) - (1 << (HAS_TM ? TML : 0))) >> 2; };  // first V4 of stage s in the lane's TMEM row
     // bit array of stage s (s>=6): word w of physical lane pl at [w*32 + pl]
     auto bits_at = [&](int s) -> uint32_t * {
         return (s < BTOP) ? (sm_bits + 32 * ((1 << (s - 5)) - 2)) : (gs_bits + 32 * (size_t)((1 << (s - 5)) - (1 << (BLO - 5))));
     };
 
-    for (unsigned long long g = blockIdx.x; g < groups; g += gridDim.x) {
+    for (unsigned long long g = gw; g < groups; g += nwarps) {
         unsigned long long frame = g * FPW + fl;
         const bool valid = frame < a.B;
         if (!valid) frame = a.B - 1;  // tail lanes decode a duplicate and write nothing
@@ -218,45 +347,79 @@ __global__ void __launch_bounds__(32, (sizeof(real) == 4) ? 32 : 24) list_decode
                 __syncwarp();
                 return;
             }
-            V4 *dst = stage_at(s) + lane;
+            // one loop body for every storage class (see f4): the source is this lane's home array in the scratch / shared memory,
+            // the channel, or its own tensor-memory row; the destination its home array or its tensor-memory row
+            const bool tsrc = in_tm(s + 1), tdst = in_tm(s);
+            const int osrc = tmoff(s + 1), odst = tmoff(s);
+            V4 *dst = tdst ? nullptr : stage_at(s) + lane;
             const V4 *src = ch4;
             int stride = 1;
-            if (s + 1 != LOGN) { src = stage_at(s + 1) + lane; stride = 32; }
+            if (!tsrc && s + 1 != LOGN) { src = stage_at(s + 1) + lane; stride = 32; }
             const V4 *src2 = src + cnt4 * stride;
+            auto load2 = [&](int i4, V4 &x, V4 &y) {
+                if (tsrc) { x = tm_ld<real>(tm, osrc + i4); y = tm_ld<real>(tm, osrc + i4 + cnt4); tm_wait_ld(); }
+                else { x = ldv(src + i4 * stride); y = ldv(src2 + i4 * stride); }
+            };
+            auto store = [&](int i4, const V4 &v) {
+                if (tdst) tm_st(tm, odst + i4, v);
+                else stv(dst + i4 * 32, v);
+            };
             // scratch / channel operands come from L2 or HBM: fetch the next pair while the current four CHKs run
-            V4 x = ldv(src), y = ldv(src2);
+            V4 x, y, x1, y1;
+            load2(0, x, y);
 #pragma unroll 1
-            for (int i4 = 0; i4 < cnt4; i4 += 2, dst += 64) {  // cnt4 >= 4 here; two steps per trip so that the operand
-                src += stride; src2 += stride;                 // registers ping-pong instead of being copied
-                const V4 x1 = ldv(src), y1 = ldv(src2);
-                stv(dst, f4<real>(x, y));
-                if (i4 + 2 < cnt4) { src += stride; src2 += stride; x = ldv(src); y = ldv(src2); }
-                stv(dst + 32, f4<real>(x1, y1));
+            for (int i4 = 0; i4 < cnt4; i4 += 2) {  // cnt4 >= 4 here; two steps per trip so that the operand registers ping-pong
+                load2(i4 + 1, x1, y1);
+                store(i4, f4<real>(x, y));
+                if (i4 + 2 < cnt4) load2(i4 + 2, x, y);
+                store(i4 + 1, f4<real>(x1, y1));
             }
+            if (tdst) tm_wait_st();
         };
 
         // ---- g-layer producing stage t (4 <= t < LOGN) from stage t+1 (via the pointer word) and the partial sums B[t]
         auto g_layer = [&](int t) {
             const int cnt4 = 1 << (t - 2);
-            V4 *dst = stage_at(t) + lane;
+            const uint32_t *bsrc = (t >= 6) ? bits_at(t) + fbase + bfield(t) : nullptr;
+            uint32_t bw = (t == 4) ? ((Blow >> 12) & 0xFFFFu) : B5;
+            // one loop body for every storage class.  Tensor-memory source: a lane reaches its own row only, so every lane loads
+            // its OWN row and the values of the slot the pointer word names arrive by shuffle.
+            const bool tsrc = in_tm(t + 1), tdst = in_tm(t);
+            const int osrc = tmoff(t + 1), odst = tmoff(t);
+            const int sl = fbase + pfield(t + 1);
+            V4 *dst = tdst ? nullptr : stage_at(t) + lane;
             const V4 *src = ch4;
             int stride = 1;
-            if (t + 1 != LOGN) { src = stage_at(t + 1) + fbase + pfield(t + 1); stride = 32; }
+            if (!tsrc && t + 1 != LOGN) { src = stage_at(t + 1) + fbase + pfield(t + 1); stride = 32; }
             const V4 *src2 = src + cnt4 * stride;
             // a g-layer is one add per node: memory bound (its operands come from the L2/HBM scratch).  Batches of four
             // node groups: eight independent 128-bit loads in flight per lane, 16 partial-sum bits per batch.
-            const uint32_t *bsrc = (t >= 6) ? bits_at(t) + fbase + bfield(t) : nullptr;
-            uint32_t bw = (t == 4) ? ((Blow >> 12) & 0xFFFFu) : B5;
 #pragma unroll 1
             for (int b = 0; b < (cnt4 >> 2); b++) {
                 if (t >= 6 && !(b & 1)) { bw = *bsrc; bsrc += 32; }
                 V4 up[4], lo[4];
+                if (tsrc) {
 #pragma unroll
-                for (int q = 0; q < 4; q++) { up[q] = ldv(src + q * stride); lo[q] = ldv(src2 + q * stride); }
+                    for (int q = 0; q < 4; q++) { up[q] = tm_ld<real>(tm, osrc + 4 * b + q); lo[q] = tm_ld<real>(tm, osrc + 4 * b + q + cnt4); }
+                    tm_wait_ld();
 #pragma unroll
-                for (int q = 0; q < 4; q++) stv(dst + q * 32, g4<real>(up[q], lo[q], (bw >> (4 * q)) & 0xFu));
-                dst += 4 * 32; src += 4 * stride; src2 += 4 * stride; bw >>= 16;
+                    for (int q = 0; q < 4; q++) if (L > 1) { up[q] = shfl_v4<real>(up[q], sl); lo[q] = shfl_v4<real>(lo[q], sl); }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; q++) { up[q] = ldv(src + q * stride); lo[q] = ldv(src2 + q * stride); }
+                    src += 4 * stride; src2 += 4 * stride;
+                }
+                if (tdst) {
+#pragma unroll
+                    for (int q = 0; q < 4; q++) tm_st(tm, odst + 4 * b + q, g4<real>(up[q], lo[q], (bw >> (4 * q)) & 0xFu));
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; q++) stv(dst + q * 32, g4<real>(up[q], lo[q], (bw >> (4 * q)) & 0xFu));
+                    dst += 4 * 32;
+                }
+                bw >>= 16;
             }
+            if (tdst) tm_wait_st();
         };
 
         // ---- one leaf: frozen -> PM only; information -> decide (SC) or fork/prune (list) ------------------
@@ -372,7 +535,20 @@ __global__ void __launch_bounds__(32, (sizeof(real) == 4) ? 32 : 24) list_decode
         };
 
         // =================================================================== the N/4 leaf groups
-        V4 *const st3 = stage_at(3), *const st4 = stage_at(4);
+        V4 *const st3 = stage_at(3);
+        // two V4s of stage s (3 or 4): of this lane's home array / of the array the pointer word names.  A tensor-memory row is
+        // reachable by its own lane only: everybody loads its own and the pointed-to slot's values arrive by shuffle.
+        auto ld_own2 = [&](int s, int ia, int ib, V4 &A, V4 &B) {
+            if (in_tm(s)) { A = tm_ld<real>(tm, tmoff(s) + ia); B = tm_ld<real>(tm, tmoff(s) + ib); tm_wait_ld(); }
+            else { const V4 *src = stage_at(s) + lane; A = ldv(src + ia * 32); B = ldv(src + ib * 32); }
+        };
+        auto ld_ptr2 = [&](int s, int ia, int ib, V4 &A, V4 &B) {
+            if (in_tm(s)) {
+                A = tm_ld<real>(tm, tmoff(s) + ia); B = tm_ld<real>(tm, tmoff(s) + ib);
+                tm_wait_ld();
+                if (L > 1) { const int sl = fbase + pfield(s); A = shfl_v4<real>(A, sl); B = shfl_v4<real>(B, sl); }
+            } else { const V4 *src = stage_at(s) + fbase + pfield(s); A = ldv(src + ia * 32); B = ldv(src + ib * 32); }
+        };
 
         // =================================================================== the frozen prefix
         // Before the first information bit a frame has ONE path and every decision is 0, so the schedule has no data dependence:
@@ -386,7 +562,9 @@ __global__ void __launch_bounds__(32, (sizeof(real) == 4) ? 32 : 24) list_decode
         if (L > 1 && a.coop_groups >= 2) {
             int P = a.coop_groups;
             if (P > N / 8) P = N / 8;               // keep the subtree inside the first half: its root is then an f-layer output
-            const int D = 32 - __clz(4 * P - 1);    // smallest subtree [0, 2^D) that holds the leaves 0..4P-1; 3 <= D <= LOGN-1
+            int D = 32 - __clz(4 * P - 1);          // smallest subtree [0, 2^D) that holds the leaves 0..4P-1; 3 <= D <= LOGN-1
+            if (HAS_TM && D < GLO) D = GLO;         // the butterfly works in ONE array shared by the frame's lanes: a global stage (a larger
+                                                    // subtree is as good: every block copied out below starts at or before leaf 4P)
             const bool inside = 4 * P < (1 << D);   // it also holds leaf 4P: the loop resumes inside it
             for (int s = LOGN - 1; s >= D; s--) f_layer(s, true);
             V4 *const buf = stage_at(D) + fbase;  // V4 i of the subtree at buf[i * 32]
@@ -403,11 +581,17 @@ __global__ void __launch_bounds__(32, (sizeof(real) == 4) ? 32 : 24) list_decode
                 }
                 __syncwarp();
                 if (inside && s >= 3) {  // the stage-s block that contains leaf 4P
-                    V4 *dst = stage_at(s) + fbase;
                     const int b4 = ((4 * P) >> s) << (s - 2);
+                    if (in_tm(s)) {  // tensor memory: every lane keeps a copy in its own row (all pointer fields say slot 0)
 #pragma unroll 1
-                    for (int q = k; q < h4; q += L) stv(dst + q * 32, ldv(buf + (b4 + q) * 32));
-                    __syncwarp();
+                        for (int q = 0; q < h4; q++) tm_st(tm, tmoff(s) + q, ldv(buf + (b4 + q) * 32));
+                        tm_wait_st();
+                    } else {
+                        V4 *dst = stage_at(s) + fbase;
+#pragma unroll 1
+                        for (int q = k; q < h4; q += L) stv(dst + q * 32, ldv(buf + (b4 + q) * 32));
+                        __syncwarp();
+                    }
                 }
             }
 #pragma unroll 1
@@ -454,18 +638,21 @@ __global__ void __launch_bounds__(32, (sizeof(real) == 4) ? 32 : 24) list_decode
             // ---- descend to stage 2 of this 4-block.  Stage 2 lives in registers only (its four values are consumed by
             // the four leaves below and cloned by shuffle); stage 3 goes through registers to the f step that follows it.
             if (j4 & 1) {  // g at stage 2 from stage 3 (via the pointer word)
-                const V4 *src = st3 + fbase + pfield(3);
-                const V4 v = g4<real>(ldv(src), ldv(src + 32), Blow & 0xFu);
+                V4 u, l;
+                ld_ptr2(3, 0, 1, u, l);
+                const V4 v = g4<real>(u, l, Blow & 0xFu);
 #pragma unroll
                 for (int e = 0; e < 4; e++) s2[e] = v.v[e];
             } else {
                 V4 a3, b3;
                 int top = 3;
                 if (j4 & 2) {  // g at stage 3 from stage 4 (via the pointer word)
-                    const V4 *src = st4 + fbase + pfield(4);
                     const uint32_t bw = Blow >> 4;
-                    a3 = g4<real>(ldv(src), ldv(src + 64), bw & 0xFu);
-                    b3 = g4<real>(ldv(src + 32), ldv(src + 96), (bw >> 4) & 0xFu);
+                    V4 u, l;
+                    ld_ptr2(4, 0, 2, u, l);
+                    a3 = g4<real>(u, l, bw & 0xFu);
+                    ld_ptr2(4, 1, 3, u, l);
+                    b3 = g4<real>(u, l, (bw >> 4) & 0xFu);
                 } else {       // a longer chain: g at the stage the finished block opens, f-layers down to stage 4, f at stage 3
                     int s = LOGN - 1;
                     top = s;
@@ -477,17 +664,35 @@ __global__ void __launch_bounds__(32, (sizeof(real) == 4) ? 32 : 24) list_decode
                     }
 #pragma unroll 1
                     for (; s >= 4; s--) f_layer(s, false);
-                    const V4 *src = st4 + lane;  // own home
-                    a3 = f4<real>(ldv(src), ldv(src + 64));
-                    b3 = f4<real>(ldv(src + 32), ldv(src + 96));
+                    V4 u, l;                 // own home
+                    ld_own2(4, 0, 2, u, l);
+                    a3 = f4<real>(u, l);
+                    ld_own2(4, 1, 3, u, l);
+                    b3 = f4<real>(u, l);
                 }
-                stv(st3 + lane, a3);
-                stv(st3 + 32 + lane, b3);
+                if (in_tm(3)) {
+                    tm_st(tm, tmoff(3), a3);
+                    tm_st(tm, tmoff(3) + 1, b3);
+                    tm_wait_st();
+                } else {
+                    stv(st3 + lane, a3);
+                    stv(st3 + 32 + lane, b3);
+                }
                 const V4 v = f4<real>(a3, b3);
 #pragma unroll
                 for (int e = 0; e < 4; e++) s2[e] = v.v[e];
                 set_pfields(top);
                 __syncwarp();
+            }
+            if (POLAR_PF_MAX && (j4 & 3) == 3 && j4 + 1 < N / 4) {
+                // the next leaf group opens with a g-layer whose source (stage t+1, whichever slot the pointer word will name after
+                // the four leaves below) is one of the frame's home arrays: every lane prefetches its own into the L1
+                const int t = __ffs(j4 + 1) + 1;
+                if (t <= POLAR_PF_MAX && t + 1 < LOGN && t + 1 >= GLO) {
+                    const V4 *pf = stage_at(t + 1) + lane;
+#pragma unroll 1
+                    for (int i4 = 0; i4 < (1 << (t - 1)); i4++) prefetch_l1(pf + i4 * 32);
+                }
             }
             ug = 0;
             const uint32_t inib = a.m.info[j4 >> 3] >> ((j4 & 7) * 4);  // which of the four leaves carry information
@@ -633,6 +838,10 @@ __global__ void __launch_bounds__(32, (sizeof(real) == 4) ? 32 : 24) list_decode
         }
         __syncwarp();
     }
+    if (HAS_TM) {  // the allocation goes back once every warp of the CTA has left its loop
+        __syncthreads();
+        if (wi == 0) tm_free(tm_base, C::TM_COLS);
+    }
 }
 
 // ---------------------------------------------------------------- dispatch
@@ -642,36 +851,66 @@ __global__ void __launch_bounds__(32, (sizeof(real) == 4) ? 32 : 24) list_decode
 #ifndef POLAR_BITS_TOP
 #define POLAR_BITS_TOP 7
 #endif
+// Tensor-memory layouts are compiled in only on request (-DPOLAR_TML=a -DPOLAR_TMH=b: fp32 LLR stages a..b-1 in TMEM).  Measured
+// on B200 (CA-SCL 1024 L=8, fp32; profiles/r2_tmem_experiments.md): stage 6 in TMEM + stages 3..5 in shared memory (7 CTAs of
+// four warps) cuts the HBM traffic by 29 % but decodes 11.2 M frames/s against 13.4 M for the layout below -- the larger code
+// (stall_no_instruction 22 % of the samples), 28 instead of 32 warps and the lost L1 outweigh the shorter memory stalls; stages
+// 3..5 in TMEM and no shared-memory stage (32 warps, 200 KB of L1): 10.2 M frames/s, 12 % more instructions (own-row loads + shuffles
+// for every pointer read, tcgen05.wait).  The code stays because the CPU emulator tests pin it and the option costs nothing.
+#ifndef POLAR_TML
+#define POLAR_TML 3
+#endif
+#ifndef POLAR_TMH
+#define POLAR_TMH 0   // TMH <= TML: no tensor memory (the product configuration)
+#endif
 // which kernel configuration serves (real, N, L); shared by the launcher below and by the CPU emulator tests
-template <typename real, int LOGN, int L>
+template <typename real, int LOGN, int L, bool ALLOW_TM = true>
 struct ListDispatchCfg {
-    static constexpr int SMEM_TOP = POLAR_SMEM_TOP, BITS_TOP = POLAR_BITS_TOP, THREADS = 32;
-    using C = ListCfg<real, LOGN, L, SMEM_TOP, BITS_TOP>;
+    static constexpr bool TM = ALLOW_TM && POLAR_TMH > POLAR_TML && sizeof(real) == 4 && LOGN >= POLAR_TMH + 1;
+    static constexpr int TML = TM ? POLAR_TML : 0, TMH = TM ? POLAR_TMH : 0;
+    static constexpr int SMEM_TOP = TM ? POLAR_TML : POLAR_SMEM_TOP, BITS_TOP = POLAR_BITS_TOP;
+    using C = ListCfg<real, LOGN, L, SMEM_TOP, BITS_TOP, TML, TMH>;
+    static constexpr int THREADS = C::THREADS;
 };
 
 #ifndef POLAR_EMU
 template <typename real, int LOGN, int L>
 struct ListDispatch {
     using D = ListDispatchCfg<real, LOGN, L>;
-    static constexpr int SMEM_TOP = D::SMEM_TOP, BITS_TOP = D::BITS_TOP;
+    static constexpr int SMEM_TOP = D::SMEM_TOP, BITS_TOP = D::BITS_TOP, TML = D::TML, TMH = D::TMH;
     using C = typename D::C;
     static cudaError_t plan(ListPlan *p)
     {
-        auto kern = list_decode_kernel<real, LOGN, L, SMEM_TOP, BITS_TOP>;
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        auto kern = list_decode_kernel<real, LOGN, L, SMEM_TOP, BITS_TOP, TML, TMH>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_CTA);
         if (e != cudaSuccess) return e;
         int nb = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 32, C::SMEM);
-        if (e != cudaSuccess) return e;
-        p->scratch_per_cta = C::GS_BYTES;
-        p->smem = C::SMEM;
+        if (C::TM_COLS) {
+            // The occupancy API answers 1 for every kernel that contains tcgen05.alloc, although CTAs do share an SM as long as
+            // their allocations fit its 512 columns (tools/ubench/tmem_occ.cu: seven 64-column CTAs run side by side): count by hand.
+            cudaFuncAttributes fa;
+            if ((e = cudaFuncGetAttributes(&fa, kern)) != cudaSuccess) return e;
+            int dev = 0;
+            cudaDeviceProp pr;
+            if ((e = cudaGetDevice(&dev)) != cudaSuccess || (e = cudaGetDeviceProperties(&pr, dev)) != cudaSuccess) return e;
+            const int regs_per_warp = ((fa.numRegs * 32 + 255) / 256) * 256;
+            const int by_regs = pr.regsPerMultiprocessor / (regs_per_warp * C::WARPS);
+            const int by_smem = (int)(pr.sharedMemPerMultiprocessor / (C::SMEM_CTA + fa.sharedSizeBytes + pr.reservedSharedMemPerBlock));
+            const int by_threads = pr.maxThreadsPerMultiProcessor / C::THREADS;
+            nb = std::min(std::min(by_regs, by_smem), std::min(by_threads, 512 / (C::TM_COLS ? C::TM_COLS : 512)));
+        } else {
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, C::THREADS, C::SMEM_CTA);
+            if (e != cudaSuccess) return e;
+        }
+        p->scratch_per_cta = C::GS_BYTES * C::WARPS;
+        p->smem = C::SMEM_CTA;
         p->ctas_per_sm = nb;
-        p->frames_per_cta = C::FPW;
+        p->frames_per_cta = C::FPW * C::WARPS;
         return cudaSuccess;
     }
     static cudaError_t launch(const ListArgs &a, int grid, cudaStream_t st)
     {
-        list_decode_kernel<real, LOGN, L, SMEM_TOP, BITS_TOP><<<grid, 32, C::SMEM, st>>>(a);
+        list_decode_kernel<real, LOGN, L, SMEM_TOP, BITS_TOP, TML, TMH><<<grid, C::THREADS, C::SMEM_CTA, st>>>(a);
         return cudaGetLastError();
     }
 };

@@ -20,7 +20,7 @@ def lib():
         _lib = C.CDLL(EMU_SO)
         vp = C.c_void_p
         _lib.emu_list_decode.argtypes = [C.c_int, C.c_int, C.c_int, vp, C.c_ulonglong, vp, vp, vp, C.c_int, C.c_int, C.c_int,
-                                         C.c_uint, vp, vp, vp]
+                                         C.c_uint, vp, vp, vp, C.c_int]
     return _lib
 
 
@@ -43,8 +43,9 @@ def crc_masks(I, N, r, poly):
     return m
 
 
-def list_decode(oracle, llr, L, use_crc, f64=True, grid=1, coop=True, count_from=0):
+def list_decode(oracle, llr, L, use_crc, f64=True, grid=1, coop=True, count_from=0, tm=1):
     """Decode llr (B,N) with the emulated list kernel; oracle supplies the code (I, inI, r, crc_poly).
+    tm: 0 = layout without tensor memory, 1 = the dispatcher's choice, 2 / 3 = a tensor-memory layout forced for any type (stages 3..5 / stage 6 only; N >= 256).
     -> (u_hat (B,N) int32, frame_info (B,) uint32, collectives executed)"""
     N = oracle.N
     n = int(np.log2(N))
@@ -63,7 +64,7 @@ def list_decode(oracle, llr, L, use_crc, f64=True, grid=1, coop=True, count_from
     fi = np.zeros(B, dtype=np.uint32)
     coll = C.c_ulonglong(0)
     rc = lib().emu_list_decode(n, L, int(f64), llr.ctypes.data, B, info.ctypes.data, cnt.ctypes.data, masks.ctypes.data, oracle.r,
-                               int(use_crc), (first // 4) if coop else 0, grid, out.ctypes.data, fi.ctypes.data, C.byref(coll))
-    assert rc == 0, "configuration (n=%d, L=%d) is not compiled into the emulator" % (n, L)
+                               int(use_crc), (first // 4) if coop else 0, grid, out.ctypes.data, fi.ctypes.data, C.byref(coll), tm)
+    assert rc == 0, "configuration (n=%d, L=%d, tm=%d) is not compiled into the emulator (rc %d)" % (n, L, tm, rc)
     bits = ((out[:, :, None] >> np.arange(32, dtype=np.uint32)[None, None, :]) & 1).reshape(B, N).astype(np.int32)
     return bits, fi, coll.value

@@ -62,3 +62,40 @@ def test_emulated_fp32_kernel_rarely_differs_from_fp64():
     want, _ = o.decode(llr)
     got, _, _ = emu_lib.list_decode(o, llr, 8, 1, f64=False)
     assert int((got != want * o.inI[None, :]).any(1).sum()) == 0
+
+
+TM_CASES = [  # program or (N, K), L, use_crc, frames, Eb/N0 -- every one with N >= 256 (a tensor-memory layout needs a scratch stage above it)
+    ("CASCL_1024_L8", 8, 1, 9, 1.0),      # 9 frames: three warps of a CTA busy, the fourth idle, a ragged last group
+    ("SC_1024", 1, 0, 40, 1.5),           # L = 1: 32 frames per warp, no pointer words
+    ("CASCL_1024_L8", 32, 1, 3, 1.0),     # 64-bit pointer words
+    ((256, 100), 4, 0, 20, 1.0),          # smallest N: the prefix subtree is raised to the first scratch stage
+    ((1024, 1000), 8, 0, 4, 4.0),         # first information bit among the first leaves: no cooperative prefix at all
+    ((1024, 40), 8, 0, 4, 1.0),           # prefix capped at N/8 groups, resumes outside the subtree
+]
+
+
+@pytest.mark.parametrize("prog,L,crc,B,snr", TM_CASES)
+def test_emulated_tensor_memory_layout_equals_oracle_f64(prog, L, crc, B, snr):
+    """The layouts with LLR stages in tensor memory (four-warp CTAs, own-row loads + shuffle for cloned pointers, the
+    copied-out prefix blocks, the raised prefix subtree), forced for fp64 in the emulator so that the oracle checks them bit for bit."""
+    o = Oracle(prog) if isinstance(prog, str) else Oracle(N=prog[0], K=prog[1], L=L)
+    rng = np.random.default_rng(77 + 7 * L + B)
+    llr = awgn_llr(rng, o.N, B, snr)
+    want, aux = o.decode(llr, kind=("sc" if L == 1 else ("cascl" if crc else "scl")), L=L)
+    for grid, tm in ((1, 2), (2, 3)):   # tm 2: stages 3..5 in tensor memory (the product layout); 3: stage 6 only, 3..5 in smem
+        got, fi, coll = emu_lib.list_decode(o, llr, L, crc, f64=True, grid=grid, tm=tm)
+        assert (got == want * o.inI[None, :]).all(), "%d of %d frames differ (grid %d, tm %d)" % (int((got != want * o.inI[None, :]).any(1).sum()), B, grid, tm)
+        if L > 1:
+            assert (((fi >> 16) & 3) == aux).all()
+
+
+@pytest.mark.parametrize("prog,L,crc", [("CASCL_1024_L8", 8, 1), ("SCL_1024", 2, 0), ("SC_1024", 1, 0)])
+def test_emulated_fp32_tensor_memory_kernel_equals_plain_fp32_kernel(prog, L, crc):
+    """fp32 with stages 3..5 in tensor memory against the fp32 product layout (no tensor memory): same arithmetic, so the
+    decisions and flags must be identical word for word, also on frames where fp32 differs from fp64."""
+    o = Oracle(prog)
+    B = 11 if L > 1 else 70
+    llr = awgn_llr(np.random.default_rng(5 + L), o.N, B, 1.0, dtype=np.float32)
+    a, fa, _ = emu_lib.list_decode(o, llr, L, crc, f64=False, grid=2, tm=0)
+    b, fb, _ = emu_lib.list_decode(o, llr, L, crc, f64=False, grid=1, tm=2)
+    assert (a == b).all() and (fa == fb).all()

@@ -269,3 +269,26 @@ def test_bp_gmatrix_stop(prog, B, ebn0):
     assert (d0[late] == d2[late]).all()
     for e in (e0, e2, e3):
         e.close()
+
+
+@pytest.mark.parametrize("prog,ebn0,over", [("CASCL_1024_L8", 1.0, {}), ("BP_128", 2.5, {"bp_early_stop": 1})])
+def test_device_frame_info_matches_host_flags(prog, ebn0, over):
+    """pg_decode_llr_device hands back the kernels' raw per-frame word (include/polargpu.h PG_INFO_*); PG_INFO_TO_FLAGS of it
+    must equal the compact flags pg_decode_llr_packed returns for the same frames, and the decisions must be the same."""
+    import torch
+    from polardecoding_b200 import Engine
+    eng = Engine(prog, real="f32", seed=3, data_mode=1, **over)
+    B = 777
+    llr, _ = eng.channel(ebn0, 0, B)
+    want, flags = eng.decode_llr(llr, packed=True)
+    d_llr = torch.from_numpy(llr).cuda()
+    d_out = torch.zeros((B, eng.N // 32), dtype=torch.int32, device="cuda")
+    d_info = torch.zeros(B, dtype=torch.int32, device="cuda")
+    eng.decode_llr_device(d_llr.data_ptr(), False, B, d_out.data_ptr(), d_info.data_ptr())
+    eng.sync()
+    w = d_info.cpu().numpy().view(np.uint32)
+    assert (d_out.cpu().numpy().view(np.uint32) == want).all()
+    assert ((w & 0xFFFF) == 0).all()                                  # no truth vector: no error count
+    assert ((((w >> 16) & 3) | ((w >> 24) << 8)) == flags).all()      # PG_INFO_TO_FLAGS
+    assert flags.any(), "the case should exercise at least one flag"
+    eng.close()
