@@ -31,9 +31,16 @@ if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "WARN"):   # t
 
 N, K_INFO = 1024, 512
 OPS_CASCL = 30016 * 27 + 35906 * 2 + 11185 * 11 + 533 * 160 + 36000 + 28000   # ~1.15 M lane-ops / frame
-OPS_BP_SWEEP = 573440                                                          # per sweep, N=1024
+OPS_BP_SWEEP = 573440                                                          # per sweep, N=1024 (20 stage passes; the kernel executes 18)
+OPS_BP_SWEEP_EXEC = OPS_BP_SWEEP * 18 // 20                                    # the two passes per sweep whose outputs nothing reads are not executed
+# the other configs[] of BASELINE.json (CHK = 27 ops, g = 2, PHI = 11, 2L-sort = 160, partial-sum XOR = 1)
+OPS_SC_128 = 448 * 29                                                          # 13.0 k
+OPS_SC_1024 = 5120 * 29                                                        # 148 k
+OPS_BP_128_SWEEP = 1792 * 28                                                   # 7 stages x 128 x 2 passes; 5.0 M per 100 sweeps
+OPS_SCL_1024 = 29572 * 27 + 35400 * 2 + 11000 * 11 + 509 * 160 + 36000         # ~1.11 M (no CRC)
 EBN0_CASCL, EBN0_BP = 2.0, 2.5
-B_CASCL, B_BP = 1 << 17, 1 << 15                                               # target frames per step (~512 MB / 128 MB of fp32 LLRs), rounded to whole waves
+# frames per step: sized so that the driver's 20 timed steps last >= 2 s on one B200 (6 GB / 200 MB of fp32 LLRs per GPU), whole waves
+B_CASCL, B_BP = 3 << 19, 3 << 14
 
 
 def peaks():
@@ -237,12 +244,15 @@ def run_gpu_arm(a):
     launches = 0
     res = {}
 
-    try:
-        traffic_db = json.load(open(os.path.join(ROOT, "profiles", "r1b_traffic.json")))
-    except Exception:
-        traffic_db = {}
+    traffic_db, traffic_src = {}, None
+    for cand in ("r2_traffic.json", "r1b_traffic.json"):
+        try:
+            traffic_db, traffic_src = json.load(open(os.path.join(ROOT, "profiles", cand))), "profiles/" + cand
+            break
+        except Exception:
+            pass
 
-    def bench_one(prog, ebn0, B, ops_per_frame, tkey=None, real="f32", e2e=True, **over):
+    def bench_one(prog, ebn0, B, ops_per_frame, tkey=None, real="f32", e2e=True, n=N, k_info=K_INFO, ops_sweep=OPS_BP_SWEEP, **over):
         nonlocal launches
         eng = Engine(prog, real=real, device=local, rank=rank, nranks=world, seed=1024, data_mode=0, **over)
         if world > 1:  # the library's own NCCL communicator: the id travels over torch.distributed
@@ -252,8 +262,9 @@ def run_gpu_arm(a):
         wave = eng.wave_frames()                      # frames a full grid decodes concurrently
         B = max(1, round(B / wave)) * wave             # whole waves: every SM stays busy until the launch ends
         st = torch.cuda.ExternalStream(eng.stream_ptr())
-        llr = torch.empty(B * N, dtype=torch.float64 if real == "f64" else torch.float32, device="cuda")
-        truth = torch.empty(B * (N // 32), dtype=torch.int32, device="cuda")
+        esz = 8 if real == "f64" else 4
+        llr = torch.empty(B * n, dtype=torch.float64 if real == "f64" else torch.float32, device="cuda")
+        truth = torch.empty(B * (n // 32), dtype=torch.int32, device="cuda")
         info = torch.empty(B, dtype=torch.int32, device="cuda")
         first = (1 << 32) + rank * B                                  # disjoint Philox frame ranges per rank
         eng.channel_device(ebn0, first, B, llr.data_ptr(), truth.data_ptr())
@@ -275,46 +286,94 @@ def run_gpu_arm(a):
         fps = world * B / (per_step * 1e-3)
         steps_total = a.steps + a.warmup
         sweeps = cnt.bp_sweeps / max(1, cnt.frames)
-        ops = ops_per_frame if ops_per_frame else OPS_BP_SWEEP * sweeps
-        out = {"frames_per_s": fps, "gbps": fps * K_INFO / 1e9, "ms_per_step": per_step, "frames_per_step": world * B,
-               "fer": cnt.err_blocks / max(1, cnt.frames), "frames_counted": int(cnt.frames), "tie_frames": int(cnt.tie_frames),
+        ops = ops_per_frame if ops_per_frame else ops_sweep * sweeps
+        byts = n * esz + 2 * (n // 8) + 4                              # algorithmic bytes per frame: LLRs in, truth in, decisions + word out
+        peak = peak_ops / 2 if real == "f64" else peak_ops             # fp64: 64 lanes per SM
+        out = {"frames_per_s": fps, "gbps": fps * k_info / 1e9, "ms_per_step": per_step, "frames_per_step": world * B,
+               "timed_s": ms / 1e3, "fer": cnt.err_blocks / max(1, cnt.frames), "frames_counted": int(cnt.frames), "tie_frames": int(cnt.tie_frames),
                "sweeps_per_frame": sweeps,
-               "roofline": {"bound": "alu", "achieved": (fps / world) * ops / 1e12, "peak": peak_ops / 1e12, "unit": "Tlaneop/s",
-                            "frac": (fps / world) * ops / peak_ops, "traffic": None, "ops_per_frame": ops, "peak_source": pk_src + " sm_max_mhz x 148 SMs x 128 lanes",
-                            "hbm_gbs": (fps / world) * (N * 4 + 2 * (N // 8) + 4) / 1e9, "hbm_frac": (fps / world) * (N * 4 + 2 * (N // 8) + 4) / 1e9 / pk["hbm_gbs"]}}
+               "roofline": {"bound": "alu", "achieved": (fps / world) * ops / 1e12, "peak": peak / 1e12, "unit": "Tlaneop/s",
+                            "frac": (fps / world) * ops / peak, "traffic": None, "ops_per_frame": ops,
+                            "peak_source": pk_src + (" sm_max_mhz x 148 SMs x 64 fp64 lanes" if real == "f64" else " sm_max_mhz x 148 SMs x 128 lanes"),
+                            "frac_of_fp32_lane_peak": (fps / world) * ops / peak_ops,
+                            "hbm_gbs": (fps / world) * byts / 1e9, "hbm_frac": (fps / world) * byts / 1e9 / pk["hbm_gbs"]}}
         tr = traffic_db.get(tkey) if tkey else None
         if tr:  # DRAM bytes of this kernel from the committed ncu --set full capture, scaled to this launch's frame count
             out["roofline"]["traffic"] = tr["dram_bytes_per_launch"] * B / tr["frames_per_launch"]
-            out["roofline"]["traffic_source"] = "profiles/r1b_traffic.json (ncu dram__bytes_read+write, %d-frame launch)" % tr["frames_per_launch"]
-            out["roofline"]["algorithmic_bytes"] = B * (N * 4 + 2 * (N // 8) + 4)
+            out["roofline"]["traffic_source"] = "%s (ncu dram__bytes_read+write, %d-frame launch)" % (traffic_src, tr["frames_per_launch"])
+            out["roofline"]["algorithmic_bytes"] = B * byts
+            out["roofline"]["traffic_over_algorithmic"] = out["roofline"]["traffic"] / (B * byts)
         assert cnt.frames == world * B * steps_total, (cnt.frames, world, B, steps_total)
         if not e2e:
             eng.close()
             del llr, truth, info
             return out
-        # ---- e2e: host LLRs (pinned) -> C ABI -> host decisions, every step
-        Be = B                                         # whole waves; the C ABI pipelines H2D of wave i+1 with the decode of wave i
-        h_llr = torch.empty(Be * N, dtype=torch.float32).pin_memory()
-        h_llr.copy_(llr[: Be * N])
-        h_out = torch.empty(Be * (N // 32), dtype=torch.int32).pin_memory()
+        # ---- e2e: host LLRs (pinned) -> C ABI -> host decisions, every step.  The host buffer holds Be <= 2^18 frames (1 GB);
+        # a step sends it B/Be times (one C-ABI call each, every call copies its inputs H2D and its results D2H)
+        reps = max(1, -(-B // (1 << 18)))
+        Be = -(-B // reps // wave) * wave
+        h_llr = torch.empty(Be * n, dtype=llr.dtype).pin_memory()
+        h_llr.copy_(llr[: Be * n])
+        h_out = torch.empty(Be * (n // 32), dtype=torch.int32).pin_memory()
         h_flags = torch.empty(Be, dtype=torch.int32).pin_memory()
-        ms_e = wall_steps(torch, dist, world, lambda: eng.decode_llr_host_ptr(h_llr.data_ptr(), False, Be, h_out.data_ptr(), h_flags.data_ptr()), a.steps, max(1, a.warmup), count)
-        fps_e = world * Be / (ms_e / a.steps * 1e-3)
-        out["e2e"] = {"value": fps_e * K_INFO / 1e9, "unit": "Gbit/s", "h2d_bytes_per_step": Be * N * 4, "d2h_bytes_per_step": Be * (N // 8) + Be * 4,
-                      "frames_per_s": fps_e, "frames_per_step": world * Be}
+
+        def e2e_step():
+            for _ in range(reps):
+                eng.decode_llr_host_ptr(h_llr.data_ptr(), real == "f64", Be, h_out.data_ptr(), h_flags.data_ptr())
+        ms_e = wall_steps(torch, dist, world, e2e_step, a.steps, max(1, min(a.warmup, 2)), count)
+        fps_e = world * Be * reps / (ms_e / a.steps * 1e-3)
+        out["e2e"] = {"value": fps_e * k_info / 1e9, "unit": "Gbit/s", "h2d_bytes_per_step": Be * reps * n * esz, "d2h_bytes_per_step": Be * reps * ((n // 8) + 4),
+                      "frames_per_s": fps_e, "frames_per_step": world * Be * reps, "calls_per_step": reps, "timed_s": ms_e / 1e3}
         eng.close()
         del llr, truth, info
         return out
 
+    def bench_simulate(prog, ebn0, seconds):
+        """pg_simulate, the Monte-Carlo loop itself (channel + decode + count + the NCCL counter exchange): frames/s with a frame
+        budget (device-side accumulation, ONE all-reduce) and with the reference's exact stopping rule (one all-reduce per round, on
+        its own stream, the next round already running)."""
+        eng = Engine(prog, real="f32", device=local, rank=rank, nranks=world, seed=1024, data_mode=0)
+        if world > 1:
+            ids = [comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            eng.comm_init(ids[0])
+        wave = eng.wave_frames()
+        eng.simulate(ebn0, 0, max_frames=world * wave * 8)                  # warm-up: buffers, NCCL channels
+        res = {}
+        rate = 12e6 * world                                                # frames/s guess used only to size the runs
+        for name, kw in (("frame_budget", {"max_frames": int(rate * seconds)}), ("exact_stop", {"target_err_blocks": int(rate * seconds * 0.0038), "exact_stop": True})):
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            c = eng.simulate(ebn0, 1 << 33, **kw)
+            dt = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dt], device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            rounds, ar = eng.simulate_stats()
+            res[name] = {"frames": int(c.frames), "err_blocks": int(c.err_blocks), "seconds": dt, "frames_per_s": c.frames / dt, "gbps": c.frames / dt * K_INFO / 1e9,
+                         "rounds": rounds, "allreduces": ar}
+        eng.close()
+        return res
+
     sampler.start()
     res["cascl"] = bench_one("CASCL_1024_L8", EBN0_CASCL, B_CASCL, OPS_CASCL, tkey="cascl")
     res["bp"] = bench_one("BP_1024", EBN0_BP, B_BP, OPS_BP_SWEEP * 100, tkey="bp")
-    res["bp_stop"] = bench_one("BP_1024", EBN0_BP, B_BP, 0, bp_early_stop=1)
-    res["bp_gm"] = bench_one("BP_1024", EBN0_BP, B_BP, 0, e2e=False, bp_early_stop=3)          # optional codeword ("G-matrix") stop rule
+    res["bp_stop"] = bench_one("BP_1024", EBN0_BP, B_BP * 4, 0, bp_early_stop=1)
+    res["bp_gm"] = bench_one("BP_1024", EBN0_BP, B_BP * 4, 0, e2e=False, bp_early_stop=3)      # optional codeword ("G-matrix") stop rule
     res["bp_h2"] = bench_one("BP_1024", EBN0_BP, B_BP, OPS_BP_SWEEP * 100, real="h2", e2e=False)   # optional packed-half mode (FER-only parity)
-    # the bit-exact (fp64) instantiation of both kernels, device-resident inputs only
-    res["cascl64"] = bench_one("CASCL_1024_L8", EBN0_CASCL, B_CASCL // 4, OPS_CASCL, real="f64", e2e=False)
-    res["bp64"] = bench_one("BP_1024", EBN0_BP, B_BP // 8, OPS_BP_SWEEP * 100, real="f64", e2e=False)
+    # the bit-exact (fp64) instantiation of both kernels: the configuration that meets north_star's "bit-exact decisions" to the letter
+    res["cascl64"] = bench_one("CASCL_1024_L8", EBN0_CASCL, B_CASCL // 3, OPS_CASCL, tkey="cascl64", real="f64")
+    res["bp64"] = bench_one("BP_1024", EBN0_BP, B_BP // 2, OPS_BP_SWEEP * 100, tkey="bp64", real="f64")
+    res["bp64_stop"] = bench_one("BP_1024", EBN0_BP, B_BP * 2, 0, real="f64", bp_early_stop=1)
+    # the other configs[] of BASELINE.json (device-resident inputs; the N = 128 programs have K = 64)
+    res["sc_128"] = bench_one("SC_128", 2.0, 1 << 22, OPS_SC_128, e2e=False, n=128, k_info=64)
+    res["bp_128"] = bench_one("BP_128", 2.5, 1 << 19, OPS_BP_128_SWEEP * 100, e2e=False, n=128, k_info=64)
+    res["sc_1024"] = bench_one("SC_1024", 2.0, 3 << 19, OPS_SC_1024, e2e=False)
+    res["scl_1024"] = bench_one("SCL_1024", 2.0, 3 << 18, OPS_SCL_1024, e2e=False)
+    sim = bench_simulate("CASCL_1024_L8", EBN0_CASCL, 1.0)
     clocks = sampler.stop()
 
     cpu = None
@@ -335,22 +394,39 @@ def run_gpu_arm(a):
                            "partition": "rank r decodes its own Philox frame range; one NCCL all-reduce of the final counters",
                            "host_numa": numa},
                 "frames_per_s": r["frames_per_s"], "fer": r["fer"], "tie_frames": r["tie_frames"], "frames_counted": r["frames_counted"],
-                "roofline": r["roofline"], "e2e": r["e2e"], "gpu_launches": launches, "clocks": clocks,
+                "timed_s": r["timed_s"], "roofline": r["roofline"], "e2e": r["e2e"], "gpu_launches": launches, "clocks": clocks,
                 "bp_1024": {"value": res["bp"]["gbps"], "unit": "Gbit/s", "frames_per_s": res["bp"]["frames_per_s"], "ms_per_step": res["bp"]["ms_per_step"],
-                            "frames_per_step": res["bp"]["frames_per_step"], "sweeps": 100, "fer": res["bp"]["fer"], "roofline": res["bp"]["roofline"],
+                            "frames_per_step": res["bp"]["frames_per_step"], "sweeps": 100, "fer": res["bp"]["fer"], "timed_s": res["bp"]["timed_s"],
+                            "roofline": dict(res["bp"]["roofline"], frac_on_executed_work=res["bp"]["roofline"]["frac"] * OPS_BP_SWEEP_EXEC / OPS_BP_SWEEP,
+                                             note="frac counts the reference's 20 stage passes per sweep; the kernel executes 18 (the two whose outputs nothing reads are skipped): frac_on_executed_work"),
                             "e2e": res["bp"]["e2e"],
                             "fixed_point_stop": {"value": res["bp_stop"]["gbps"], "frames_per_s": res["bp_stop"]["frames_per_s"],
                                                  "sweeps_per_frame": res["bp_stop"]["sweeps_per_frame"], "fer": res["bp_stop"]["fer"],
-                                                 "roofline": res["bp_stop"]["roofline"], "note": "same decisions as 100 sweeps (bit-exact stop)"},
+                                                 "roofline": res["bp_stop"]["roofline"], "e2e": res["bp_stop"]["e2e"], "note": "same decisions as 100 sweeps (bit-exact stop)"},
                             "gmatrix_stop": {"value": res["bp_gm"]["gbps"], "frames_per_s": res["bp_gm"]["frames_per_s"],
                                              "sweeps_per_frame": res["bp_gm"]["sweeps_per_frame"], "fer": res["bp_gm"]["fer"],
                                              "note": "optional flag (bp_early_stop bit 1): stop when the decisions form a codeword; not in the reference, FER-level parity only"},
                             "half2_mode": {"value": res["bp_h2"]["gbps"], "frames_per_s": res["bp_h2"]["frames_per_s"], "fer": res["bp_h2"]["fer"],
                                            "frac_of_fp32_lane_roofline": res["bp_h2"]["roofline"]["frac"],
                                            "note": "PG_REAL_H2, optional flag: two frames per __half2, a numerically different decoder judged on FER only (not the headline)"}}}
-        line["f64_parity_mode"] = {"note": "same kernels instantiated in double: decisions bit-exact with the reference (tests/test_gpu_parity.py)",
-                                   "cascl_1024_l8": {"value": res["cascl64"]["gbps"], "unit": "Gbit/s", "frames_per_s": res["cascl64"]["frames_per_s"], "fer": res["cascl64"]["fer"]},
-                                   "bp_1024": {"value": res["bp64"]["gbps"], "unit": "Gbit/s", "frames_per_s": res["bp64"]["frames_per_s"], "fer": res["bp64"]["fer"]}}
+        def leg(x, **extra):
+            d = {"value": x["gbps"], "unit": "Gbit/s", "frames_per_s": x["frames_per_s"], "ms_per_step": x["ms_per_step"], "frames_per_step": x["frames_per_step"],
+                 "timed_s": x["timed_s"], "fer": x["fer"], "roofline": x["roofline"]}
+            if "e2e" in x:
+                d["e2e"] = x["e2e"]
+            d.update(extra)
+            return d
+        line["f64_parity_mode"] = {"note": "same kernels instantiated in double: decisions bit-exact with the reference (tests/test_gpu_parity.py); roofline.frac is "
+                                           "against the fp64 peak (64 lanes per SM), frac_of_fp32_lane_peak against the line's headline peak; e2e sends fp64 LLRs (8 KiB per frame)",
+                                   "cascl_1024_l8": leg(res["cascl64"]),
+                                   "bp_1024": leg(res["bp64"], sweeps=100,
+                                                  fixed_point_stop=leg(res["bp64_stop"], sweeps_per_frame=res["bp64_stop"]["sweeps_per_frame"],
+                                                                       note="bit-exact AND early-stopped: the sweeps after the fixed point change nothing (BP_1024.c:393 runs them anyway)"))}
+        line["configs"] = {"note": "the other configs[] of BASELINE.json, device-resident inputs, fp32; ops_per_frame from SURVEY 8d",
+                           "sc_128": leg(res["sc_128"]), "bp_128": leg(res["bp_128"], sweeps=100), "sc_1024": leg(res["sc_1024"]), "scl_1024": leg(res["scl_1024"])}
+        line["simulate"] = dict(sim, note="pg_simulate = channel + decode + count + counter exchange, wall clock, max over ranks",
+                                collective=("ncclAllReduce (sum) of %d x 8 u64 per round on a second stream; ONE at the end of a frame-budget run" % world) if world > 1 else "none (1 rank)",
+                                frac_of_kernel_rate={k: v["frames_per_s"] / r["frames_per_s"] for k, v in sim.items()})
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)

@@ -50,6 +50,7 @@ enum pg_real { PG_REAL_F64 = 0, /* parity mode: bit-exact with the reference's d
                PG_REAL_F32 = 1, /* throughput mode */
                PG_REAL_H2 = 2   /* BP only, optional: messages as packed half (two frames per __half2); a numerically
                                    different decoder, judged on FER only; LLR buffers stay float */ };
+enum pg_llr_format { PG_LLR_F32 = 0, PG_LLR_F64 = 1, PG_LLR_F16 = 2 }; /* the `llr_is_f64` argument of the streaming calls */
 enum pg_data { PG_DATA_PN63 = 0,  /* the reference's PN-63 payload, phase m = frame*(K%63) mod 63 (SC_128.c:126-138,180,214) */
                PG_DATA_PHILOX = 1 /* random payload from the Philox stream */ };
 
@@ -88,7 +89,9 @@ typedef struct pg_counters {
 } pg_counters;
 
 /* fill *p with the defaults of one of the reference programs: "SC_128", "SC_1024", "SC_128_fag", "SCL_128",
- * "SCL_1024", "SCL_128_fag", "CASCL_128", "CASCL_1024_L8", "CASCL_1024_sys", "BP_128", "BP_1024", "BP_128_fag", "BPr_128" */
+ * "SCL_1024", "SCL_128_fag", "CASCL_128", "CASCL_1024_L8", "CASCL_1024_sys", "BP_128", "BP_1024", "BP_128_fag", "BPr_128";
+ * plus "CASCL_128_sys": the systematic CRC-6 variant of CASCL_128 whose parity table is the reference's CRC_6.dat and whose
+ * result files are result_128_fag/CAL8_0.dat / CAL32_0.dat (its source is not in the reference repository) */
 int pg_params_preset(pg_params *p, const char *program);
 
 int pg_create(const pg_params *p, pg_ctx **out);
@@ -99,8 +102,10 @@ const char *pg_last_error(const pg_ctx *ctx); /* ctx may be NULL: error of the l
 int pg_info_set(const pg_ctx *ctx, int *I_out, uint8_t *inI_out);
 
 /* ---- streaming mode: decode B frames of caller-supplied LLRs -------------------------------------------
- * llr      [B][N] row-major, natural bit order; element type by llr_is_f64 (converted to the context's
- *          arithmetic type on the device).  HOST pointer (pinned or pageable); copied H2D inside the call.
+ * llr      [B][N] row-major, natural bit order; element type by llr_is_f64 = one of PG_LLR_F32 (0), PG_LLR_F64 (1) or
+ *          PG_LLR_F16 (2: IEEE binary16, 2 KiB per N = 1024 frame -- half the bytes a streaming host has to move; a quantised
+ *          input, so judged on FER like PG_REAL_H2, not bit-exact); converted to the context's arithmetic type on the
+ *          device.  HOST pointer (pinned or pageable); copied H2D inside the call.
  * u_hat    [B][N] one byte per bit (0/1), HOST, may be NULL.
  * flags    [B] per-frame: bit0 tie frame, bit1 no CRC pass; bits 8..15 BP sweeps executed. HOST, may be NULL. */
 int pg_decode_llr(pg_ctx *ctx, const void *llr, int llr_is_f64, size_t B, uint8_t *u_hat, uint32_t *flags);
@@ -126,7 +131,8 @@ int pg_decode_llr_device(pg_ctx *ctx, const void *d_llr, int llr_is_f64, size_t 
 
 /* device-resident variant with the on-device error count: d_truth_packed ([B][N/32], e.g. from pg_channel_device) is
  * compared on the counted positions; block/bit errors, tie and CRC-fail frames are ADDED to the context's device
- * counters (read with pg_counters_read).  d_u_hat_packed / d_frame_info may be NULL.  Asynchronous on the ctx stream. */
+ * counters (read with pg_counters_read; no other call touches them).  d_u_hat_packed / d_frame_info may be NULL.
+ * Asynchronous on the ctx stream. */
 int pg_decode_count_device(pg_ctx *ctx, const void *d_llr, int llr_is_f64, size_t B, const uint32_t *d_truth_packed,
                            uint32_t *d_u_hat_packed, uint32_t *d_frame_info);
 int pg_counters_read(pg_ctx *ctx, pg_counters *out, int reset); /* synchronises the ctx stream */
@@ -149,6 +155,10 @@ int pg_channel_device(pg_ctx *ctx, double ebn0_db, uint64_t first_frame, size_t 
  * per-round counters are combined with one NCCL all-reduce (pg_comm_init first).  out = global counters. */
 int pg_simulate(pg_ctx *ctx, double ebn0_db, uint64_t first_frame, uint64_t target_err_blocks, uint64_t max_frames,
                 int exact_stop, pg_counters *out);
+/* The loop is pipelined: the next round is already queued on the GPU while the host (and NCCL, on a second stream) finish the
+ * previous one; with a frame budget only (target_err_blocks == 0) the counters accumulate on the device and the ranks are combined
+ * by ONE all-reduce at the end.  pg_simulate_stats: rounds launched and all-reduces issued by the last pg_simulate call. */
+int pg_simulate_stats(const pg_ctx *ctx, uint64_t *rounds, uint64_t *allreduces);
 
 /* fixed-size batch, no stopping rule, no collective: frames [first_frame, first_frame+B) on this GPU; counters ADDED to *acc.
  * frame_err (HOST, [B], may be NULL): per frame, number of wrong counted bits (0 = frame correct).  Used by bench and tests. */
@@ -179,6 +189,12 @@ int pg_allreduce_counters(pg_ctx *ctx, pg_counters *c); /* in place, sum over ra
 int pg_partition(uint64_t round_first, uint64_t chunk, int nranks, int rank, uint64_t budget, uint64_t *start, uint64_t *count);
 int pg_merge_round(const pg_counters *round, int nranks, uint64_t target, int exact_stop, pg_counters *acc, int *cut_rank, uint64_t *need);
 int pg_truncate_info(const uint32_t *frame_info, size_t nframes, uint64_t need, pg_counters *part);
+
+/* ---- CRC parity table in the reference's file format (/root/reference/CRC_6.dat: K rows of r integers, row i = coefficients
+ * c0..c(r-1) of D^(r+i) mod g(D); UTF-16 with BOM or ASCII).  Validates that the file is the table of ONE polynomial, returns it
+ * in the pg_params.crc_poly convention and, if rows != NULL, the K parity rows as r-bit words (bit b = coefficient of D^b).
+ * Host only, no device needed.  The systematic encoder/CRC check (crc_systematic = 1) derives the same rows from crc_poly. */
+int pg_crc_table_load(const char *path, int K, int r, uint64_t *crc_poly, uint32_t *rows);
 
 /* ---- introspection for benches ------------------------------------------------------------------------ */
 /* frames one full grid of the decode kernel holds at a time (resident CTAs x frames per CTA): batch sizes that are a

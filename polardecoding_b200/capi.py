@@ -10,6 +10,7 @@ LIB_PATH = os.environ.get("POLARGPU_LIB") or os.path.join(HERE, "libpolargpu.so"
 
 PROGRAMS = ["SC_128", "SC_1024", "SC_128_fag", "SCL_128", "SCL_1024", "SCL_128_fag", "CASCL_128", "CASCL_1024_L8",
             "CASCL_1024_sys", "BP_128", "BP_1024", "BP_128_fag", "BPr_128"]
+EXTRA_PROGRAMS = ["CASCL_128_sys"]   # a variant the reference documents by its data (CRC_6.dat) and result files only
 
 PG_DEC_SC, PG_DEC_SCL, PG_DEC_CASCL, PG_DEC_BP = 0, 1, 2, 3
 PG_REAL_F64, PG_REAL_F32, PG_REAL_H2 = 0, 1, 2
@@ -61,6 +62,7 @@ def load_library():
     lib.pg_channel_device.argtypes = [vp, C.c_double, C.c_uint64, C.c_size_t, vp, vp]
     lib.pg_channel.argtypes = [vp, C.c_double, C.c_uint64, C.c_size_t, vp, vp]
     lib.pg_simulate.argtypes = [vp, C.c_double, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(PgCounters)]
+    lib.pg_simulate_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.pg_simulate_batch.argtypes = [vp, C.c_double, C.c_uint64, C.c_size_t, C.POINTER(PgCounters), vp]
     lib.pg_bpr_config.argtypes = [vp, C.POINTER(C.c_int), C.c_int]
     lib.pg_bpr_read.argtypes = [vp, C.POINTER(C.c_uint64)]
@@ -128,19 +130,20 @@ class Engine:
             raise RuntimeError("%s failed (%d): %s" % (what, rc, self.lib.pg_last_error(self.ctx).decode()))
 
     def decode_llr(self, llr, packed=False):
-        """llr (B,N) float32 or float64 host array -> (u_hat (B,N) uint8 | (B,N/32) uint32, flags (B,) uint32)."""
+        """llr (B,N) float32, float64 or float16 host array -> (u_hat (B,N) uint8 | (B,N/32) uint32, flags (B,) uint32)."""
         llr = np.ascontiguousarray(llr)
-        if llr.dtype not in (np.float32, np.float64):
+        if llr.dtype not in (np.float32, np.float64, np.float16):
             llr = llr.astype(np.float64)
         llr = llr.reshape(-1, self.N)
         B = llr.shape[0]
+        fmt = {np.dtype(np.float32): 0, np.dtype(np.float64): 1, np.dtype(np.float16): 2}[llr.dtype]   # PG_LLR_F32 / F64 / F16
         flags = np.zeros(B, dtype=np.uint32)
         if packed:
             out = np.zeros((B, self.N // 32), dtype=np.uint32)
-            rc = self.lib.pg_decode_llr_packed(self.ctx, llr.ctypes.data, int(llr.dtype == np.float64), B, out.ctypes.data, flags.ctypes.data)
+            rc = self.lib.pg_decode_llr_packed(self.ctx, llr.ctypes.data, fmt, B, out.ctypes.data, flags.ctypes.data)
         else:
             out = np.zeros((B, self.N), dtype=np.uint8)
-            rc = self.lib.pg_decode_llr(self.ctx, llr.ctypes.data, int(llr.dtype == np.float64), B, out.ctypes.data, flags.ctypes.data)
+            rc = self.lib.pg_decode_llr(self.ctx, llr.ctypes.data, fmt, B, out.ctypes.data, flags.ctypes.data)
         self._check(rc, "pg_decode_llr")
         return out, flags
 
@@ -179,6 +182,12 @@ class Engine:
         self._check(rc, "pg_simulate")
         return out
 
+    def simulate_stats(self):
+        """(rounds launched, all-reduces issued) by the last simulate() call"""
+        r, a = C.c_uint64(), C.c_uint64()
+        self._check(self.lib.pg_simulate_stats(self.ctx, C.byref(r), C.byref(a)), "pg_simulate_stats")
+        return int(r.value), int(a.value)
+
     # ---- device-pointer calls (pointers are plain integers, e.g. torch.Tensor.data_ptr())
     def channel_device(self, ebn0_db, first_frame, B, d_llr, d_u_packed):
         self._check(self.lib.pg_channel_device(self.ctx, float(ebn0_db), int(first_frame), B, d_llr, d_u_packed), "pg_channel_device")
@@ -195,7 +204,7 @@ class Engine:
         return out
 
     def decode_llr_host_ptr(self, llr_ptr, llr_is_f64, B, out_packed_ptr, flags_ptr=None):
-        """pg_decode_llr_packed on raw host pointers (pinned buffers owned by the caller)"""
+        """pg_decode_llr_packed on raw host pointers (pinned buffers owned by the caller); llr_is_f64: False/True or a PG_LLR_* code"""
         self._check(self.lib.pg_decode_llr_packed(self.ctx, llr_ptr, int(llr_is_f64), B, out_packed_ptr, flags_ptr), "pg_decode_llr_packed")
 
     def stream_ptr(self):

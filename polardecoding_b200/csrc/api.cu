@@ -50,6 +50,9 @@ struct NcclApi {
 NcclApi g_nccl;
 
 int ilog2(int v) { int k = 0; while ((1 << k) < v) k++; return k; }
+// LLR element formats of the streaming calls (PG_LLR_*)
+inline bool llr_fmt_ok(int f) { return f == PG_LLR_F32 || f == PG_LLR_F64 || f == PG_LLR_F16; }
+inline size_t llr_esz(int f) { return f == PG_LLR_F64 ? 8 : (f == PG_LLR_F16 ? 2 : 4); }
 
 // the public PG_INFO_* layout (include/polargpu.h) is the kernels' frame-info word (engine.h)
 static_assert(PG_INFO_TIE == polar::kInfoTie && PG_INFO_CRC_FAIL == polar::kInfoCrcFail, "frame-info layout");
@@ -71,13 +74,15 @@ struct pg_ctx {
 
     cudaStream_t st = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // channel start/stop, decode start/stop
-    bool ev_ch = false, ev_dec = false;
+    bool ev_ch = false, ev_dec = false, ev_suppress = false;
     uint64_t launches = 0;
 
     // device tables
     uint16_t *d_I = nullptr;
     uint32_t *d_crc_masks = nullptr, *d_crc_sys = nullptr;
     unsigned long long *d_counters = nullptr, *d_queue = nullptr, *d_bpr = nullptr;
+    unsigned long long *d_cnt2 = nullptr;   // counters of the calls that return their own sums (pg_simulate*, pg_decode_llr_counted);
+                                            // d_counters belongs to pg_decode_count_device / pg_counters_read alone
     int bpr_ns = 0, bpr_samples[8] = {0};
 
     // work buffers for `cap` frames
@@ -97,7 +102,9 @@ struct pg_ctx {
     // BP runs one
     cudaStream_t st_copy = nullptr, st_lane[kPipeLanes] = {};  // st_lane[0] is st
     cudaEvent_t ev_h2d[kPipeBufs] = {}, ev_free[kPipeBufs] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[kPipeLanes] = {};
     size_t pipe_cap = 0;
+    bool pipe_ready = false;
     void *p_llr[kPipeBufs] = {}, *p_in[kPipeBufs] = {};
     uint32_t *p_uhat[kPipeBufs] = {}, *p_info[kPipeBufs] = {};
     uint8_t *p_bytes[kPipeBufs] = {};
@@ -105,6 +112,16 @@ struct pg_ctx {
 
     ncclComm_t comm = nullptr;
     unsigned long long *d_xchg = nullptr;  // nranks*CNT_N
+    // pipelined Monte-Carlo loop (pg_simulate): a ring of round slots, the counter exchange on its own stream
+    static constexpr int kRing = 3;
+    cudaStream_t st_comm = nullptr;
+    unsigned long long *d_rc[kRing] = {};      // this rank's counters of the round in the slot (CNT_N)
+    unsigned long long *d_xm[kRing] = {};      // [nranks][CNT_N] exchange matrix of the round
+    unsigned long long *h_xm[kRing] = {};      // pinned copy of the reduced matrix
+    uint32_t *d_rinfo[kRing] = {};             // per-frame words of the round (exact stop), ring_cap frames each
+    size_t ring_cap = 0;
+    cudaEvent_t ev_round[kRing] = {}, ev_xdone[kRing] = {};
+    uint64_t sim_rounds = 0, sim_allreduces = 0;   // statistics of the last pg_simulate call
 };
 
 #define CU(call)                                                                                 \
@@ -134,6 +151,7 @@ extern "C" int pg_params_preset(pg_params *p, const char *prog)
     else if (s == "SCL_128" || s == "SCL_128_fag") { code(128, 64, 0, 0, 0); p->decoder = PG_DEC_SCL; p->list_size = 8; }
     else if (s == "SCL_1024") { code(1024, 512, 0, 0, 0); p->decoder = PG_DEC_SCL; p->list_size = 8; }
     else if (s == "CASCL_128") { code(128, 64, 6, PG_CRC6_POLY, 0); p->decoder = PG_DEC_CASCL; p->list_size = 8; }
+    else if (s == "CASCL_128_sys") { code(128, 64, 6, PG_CRC6_POLY, 1); p->decoder = PG_DEC_CASCL; p->list_size = 8; p->count_from = 6; }
     else if (s == "CASCL_1024_L8") { code(1024, 512, 24, PG_CRC24_POLY, 0); p->decoder = PG_DEC_CASCL; p->list_size = 8; }
     else if (s == "CASCL_1024_sys") { code(1024, 512, 24, PG_CRC24_POLY, 1); p->decoder = PG_DEC_CASCL; p->list_size = 8; p->count_from = 24; }
     else if (s == "BP_128" || s == "BP_128_fag") { code(128, 64, 0, 0, 0); p->decoder = PG_DEC_BP; p->iter_max = 100; }
@@ -173,18 +191,31 @@ static void free_buffers(pg_ctx *ctx)
     ctx->cap = 0;
 }
 
+static int ensure_lanes(pg_ctx *ctx)
+{
+    if (!ctx->pipe_ready) {  // streams and events: all or nothing (a partial set is completed on the next call)
+        if (!ctx->st_copy) CU(cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking));
+        ctx->st_lane[0] = ctx->st;
+        for (int l = 1; l < kPipeLanes; l++)
+            if (!ctx->st_lane[l]) CU(cudaStreamCreateWithFlags(&ctx->st_lane[l], cudaStreamNonBlocking));
+        for (int s = 0; s < kPipeBufs; s++) {
+            if (!ctx->ev_h2d[s]) CU(cudaEventCreateWithFlags(&ctx->ev_h2d[s], cudaEventDisableTiming));
+            if (!ctx->ev_free[s]) CU(cudaEventCreateWithFlags(&ctx->ev_free[s], cudaEventDisableTiming));
+        }
+        for (int l = 0; l < kPipeLanes; l++)
+            if (!ctx->ev_join[l]) CU(cudaEventCreateWithFlags(&ctx->ev_join[l], cudaEventDisableTiming));
+        if (!ctx->ev_fork) CU(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+        ctx->pipe_ready = true;
+    }
+    return PG_OK;
+}
+
 static int ensure_pipe(pg_ctx *ctx, size_t frames, bool want_bytes)
 {
-    if (!ctx->st_copy) {
-        CU(cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking));
-        ctx->st_lane[0] = ctx->st;
-        for (int l = 1; l < kPipeLanes; l++) CU(cudaStreamCreateWithFlags(&ctx->st_lane[l], cudaStreamNonBlocking));
-        for (int s = 0; s < kPipeBufs; s++) {
-            CU(cudaEventCreateWithFlags(&ctx->ev_h2d[s], cudaEventDisableTiming));
-            CU(cudaEventCreateWithFlags(&ctx->ev_free[s], cudaEventDisableTiming));
-        }
-    }
+    int rcl = ensure_lanes(ctx);
+    if (rcl) return rcl;
     if (frames <= ctx->pipe_cap && (!want_bytes || ctx->p_bytes[0])) return PG_OK;
+    ctx->pipe_cap = 0;  // nothing is usable until every buffer set below exists at the new size
     const size_t N = ctx->p.N, W = ctx->W;
     for (int s = 0; s < kPipeBufs; s++) {
         cudaFree(ctx->p_llr[s]); cudaFree(ctx->p_in[s]); cudaFree(ctx->p_uhat[s]); cudaFree(ctx->p_info[s]); cudaFree(ctx->p_bytes[s]);
@@ -288,6 +319,8 @@ extern "C" int pg_create(const pg_params *p, pg_ctx **out)
     }
     CUC(cudaMalloc(&ctx->d_counters, CNT_N * 8));
     CUC(cudaMemset(ctx->d_counters, 0, CNT_N * 8));
+    CUC(cudaMalloc(&ctx->d_cnt2, CNT_N * 8));
+    CUC(cudaMemset(ctx->d_cnt2, 0, CNT_N * 8));
     CUC(cudaMalloc(&ctx->d_queue, 8));
     CUC(cudaMalloc(&ctx->d_bpr, 8 * 16 * 8));
     CUC(cudaMemset(ctx->d_bpr, 0, 8 * 16 * 8));
@@ -341,10 +374,21 @@ extern "C" void pg_destroy(pg_ctx *ctx)
         if (ctx->ev_h2d[s]) cudaEventDestroy(ctx->ev_h2d[s]);
         if (ctx->ev_free[s]) cudaEventDestroy(ctx->ev_free[s]);
     }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    for (int l = 0; l < kPipeLanes; l++)
+        if (ctx->ev_join[l]) cudaEventDestroy(ctx->ev_join[l]);
+    if (ctx->st_comm) cudaStreamSynchronize(ctx->st_comm);
+    for (int r = 0; r < pg_ctx::kRing; r++) {
+        cudaFree(ctx->d_rc[r]); cudaFree(ctx->d_xm[r]); cudaFree(ctx->d_rinfo[r]);
+        if (ctx->h_xm[r]) cudaFreeHost(ctx->h_xm[r]);
+        if (ctx->ev_round[r]) cudaEventDestroy(ctx->ev_round[r]);
+        if (ctx->ev_xdone[r]) cudaEventDestroy(ctx->ev_xdone[r]);
+    }
+    if (ctx->st_comm) cudaStreamDestroy(ctx->st_comm);
     if (ctx->st_copy) cudaStreamDestroy(ctx->st_copy);
     for (int l = 1; l < kPipeLanes; l++)
         if (ctx->st_lane[l]) cudaStreamDestroy(ctx->st_lane[l]);
-    cudaFree(ctx->d_I); cudaFree(ctx->d_crc_masks); cudaFree(ctx->d_crc_sys); cudaFree(ctx->d_counters); cudaFree(ctx->d_queue);
+    cudaFree(ctx->d_I); cudaFree(ctx->d_crc_masks); cudaFree(ctx->d_crc_sys); cudaFree(ctx->d_counters); cudaFree(ctx->d_cnt2); cudaFree(ctx->d_queue);
     cudaFree(ctx->d_bpr); cudaFree(ctx->d_scratch); cudaFree(ctx->d_xchg);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -404,16 +448,16 @@ static int run_channel(pg_ctx *ctx, double ebn0_db, uint64_t first, size_t B, bo
 
 // decode B frames on stream `st` with at most `grid_cap` CTAs that use the scratch slots [cta_off, cta_off + grid_cap)
 static int run_decode_on(pg_ctx *ctx, cudaStream_t st, int grid_cap, int cta_off, const void *d_llr, size_t B, const uint32_t *d_truth,
-                         uint32_t *d_uhat, uint32_t *d_info, bool count)
+                         uint32_t *d_uhat, uint32_t *d_info, unsigned long long *d_cnt)
 {
     const pg_params &p = ctx->p;
-    const bool timed = (st == ctx->st);
+    const bool timed = (st == ctx->st) && !ctx->ev_suppress;
     if (timed) CU(cudaEventRecord(ctx->ev[2], st));
     if (p.decoder == PG_DEC_BP) {
         BpArgs a;
         std::memset(&a, 0, sizeof(a));
         a.llr = d_llr; a.truth = d_truth; a.u_hat = d_uhat; a.frame_info = d_info;
-        a.counters = count ? ctx->d_counters : nullptr;
+        a.counters = d_cnt;
         a.queue = ctx->d_queue;
         a.bpr_E = ctx->bpr_ns ? ctx->d_bpr : nullptr;
         a.bpr_ns = ctx->bpr_ns;
@@ -433,7 +477,7 @@ static int run_decode_on(pg_ctx *ctx, cudaStream_t st, int grid_cap, int cta_off
         ListArgs a;
         std::memset(&a, 0, sizeof(a));
         a.llr = d_llr; a.truth = d_truth; a.u_hat = d_uhat; a.frame_info = d_info;
-        a.counters = count ? ctx->d_counters : nullptr;
+        a.counters = d_cnt;
         a.gscratch = ctx->d_scratch ? (char *)ctx->d_scratch + (size_t)cta_off * ctx->scratch_per_cta : nullptr;
         a.crc_masks = ctx->d_crc_masks;
         a.B = B; a.r = p.crc_bits; a.use_crc = (p.decoder == PG_DEC_CASCL);
@@ -455,21 +499,58 @@ static int run_decode_on(pg_ctx *ctx, cudaStream_t st, int grid_cap, int cta_off
     return debug_sync(ctx, "decode");
 }
 
+// Device-resident decode of B frames, asynchronous on the ctx stream.  One full-grid launch -- except for the fp64 list decoders:
+// their persistent warps slow down once they have drifted out of phase (twice the scratch bytes per frame; measured with
+// tools/lane_probe.py: 4.03 M frames/s in one launch of 32 waves, 4.40 M in one-wave launches, 5.02 M in quarter-wave launches on
+// four streams, where every warp decodes one frame group and leaves), so they run as short quarter-grid launches on four
+// streams that fork from and join the ctx stream.  fp32 is indifferent to the launch shape (13.2 / 13.2 / 13.0 M).
+static int run_decode_dev(pg_ctx *ctx, const void *d_llr, size_t B, const uint32_t *d_truth, uint32_t *d_uhat, uint32_t *d_info,
+                          unsigned long long *d_cnt)
+{
+    const bool lanes_ok = ctx->p.decoder != PG_DEC_BP && ctx->f64 && ctx->grid >= 4 * kPipeLanes && !getenv("POLARGPU_NO_LANES");
+    const size_t quarter = (size_t)(ctx->grid / kPipeLanes) * ctx->frames_per_cta;
+    if (!lanes_ok || B <= quarter) return run_decode_on(ctx, ctx->st, ctx->grid, 0, d_llr, B, d_truth, d_uhat, d_info, d_cnt);
+    int rc = ensure_lanes(ctx);
+    if (rc) return rc;
+    const size_t N = ctx->p.N, W = ctx->W, esz = 8;
+    const int lane_grid = ctx->grid / kPipeLanes;
+    CU(cudaEventRecord(ctx->ev[2], ctx->st));
+    CU(cudaEventRecord(ctx->ev_fork, ctx->st));
+    for (int l = 1; l < kPipeLanes; l++) CU(cudaStreamWaitEvent(ctx->st_lane[l], ctx->ev_fork, 0));
+    size_t i = 0;
+    ctx->ev_suppress = true;  // the events around the whole fork/join region time this decode, not one of its launches
+    for (size_t off = 0; off < B && !rc; off += quarter, i++) {
+        const size_t b = std::min(quarter, B - off);
+        const int lane = (int)(i % kPipeLanes);
+        rc = run_decode_on(ctx, ctx->st_lane[lane], lane_grid, lane * lane_grid, (const char *)d_llr + off * N * esz, b, d_truth ? d_truth + off * W : nullptr,
+                           d_uhat ? d_uhat + off * W : nullptr, d_info ? d_info + off : nullptr, d_cnt);
+    }
+    ctx->ev_suppress = false;
+    if (rc) return rc;
+    for (int l = 1; l < kPipeLanes; l++) {
+        CU(cudaEventRecord(ctx->ev_join[l], ctx->st_lane[l]));
+        CU(cudaStreamWaitEvent(ctx->st, ctx->ev_join[l], 0));
+    }
+    CU(cudaEventRecord(ctx->ev[3], ctx->st));
+    ctx->ev_dec = true;
+    return PG_OK;
+}
+
 static int run_decode(pg_ctx *ctx, const void *d_llr, size_t B, const uint32_t *d_truth, uint32_t *d_uhat, uint32_t *d_info, bool count)
 {
-    return run_decode_on(ctx, ctx->st, ctx->grid, 0, d_llr, B, d_truth, d_uhat, d_info, count);
+    return run_decode_dev(ctx, d_llr, B, d_truth, d_uhat, d_info, count ? ctx->d_counters : nullptr);
 }
 
 extern "C" int pg_decode_llr_device(pg_ctx *ctx, const void *d_llr, int llr_is_f64, size_t B, uint32_t *d_u_hat_packed, uint32_t *d_frame_info)
 {
-    if (!ctx || !d_llr) return PG_ERR_ARG;
+    if (!ctx || !d_llr || !llr_fmt_ok(llr_is_f64)) return PG_ERR_ARG;
     if (B == 0) return PG_OK;
     CU(cudaSetDevice(ctx->p.device));
     const void *src = d_llr;
-    if ((llr_is_f64 != 0) != ctx->f64) {
+    if (llr_is_f64 != (ctx->f64 ? PG_LLR_F64 : PG_LLR_F32)) {
         int rc = ensure_capacity(ctx, B);
         if (rc) return rc;
-        CU(launch_convert_llr(d_llr, llr_is_f64 != 0, ctx->d_llr, ctx->f64, B * (size_t)ctx->p.N, ctx->st));
+        CU(launch_convert_llr(d_llr, llr_is_f64, ctx->d_llr, ctx->f64, B * (size_t)ctx->p.N, ctx->st));
         ctx->launches++;
         src = ctx->d_llr;
     }
@@ -482,7 +563,7 @@ extern "C" int pg_decode_count_device(pg_ctx *ctx, const void *d_llr, int llr_is
     if (!ctx || !d_llr) return PG_ERR_ARG;
     if (B == 0) return PG_OK;
     CU(cudaSetDevice(ctx->p.device));
-    if ((llr_is_f64 != 0) != ctx->f64) { ctx->err = "pg_decode_count_device: LLR type must be the context's arithmetic type"; return PG_ERR_ARG; }
+    if (llr_is_f64 != (ctx->f64 ? PG_LLR_F64 : PG_LLR_F32)) { ctx->err = "pg_decode_count_device: LLR type must be the context's arithmetic type"; return PG_ERR_ARG; }
     return run_decode(ctx, d_llr, B, d_truth_packed, d_u_hat_packed, d_frame_info, true);
 }
 
@@ -514,11 +595,11 @@ static uint64_t wave_frames(const pg_ctx *ctx)
 // two buffer sets: the H2D copy of chunk i+1 (copy stream) overlaps the decode + D2H of chunk i (compute stream).
 static int decode_host(pg_ctx *ctx, const void *llr, int llr_is_f64, size_t B, uint8_t *u_hat, uint32_t *u_hat_packed, uint32_t *flags)
 {
-    if (!ctx || !llr) return PG_ERR_ARG;
+    if (!ctx || !llr || !llr_fmt_ok(llr_is_f64)) return PG_ERR_ARG;
     CU(cudaSetDevice(ctx->p.device));
     const size_t N = ctx->p.N, W = ctx->W;
-    const size_t esz = llr_is_f64 ? 8 : 4;
-    const bool conv = (llr_is_f64 != 0) != ctx->f64;
+    const size_t esz = llr_esz(llr_is_f64);
+    const bool conv = llr_is_f64 != (ctx->f64 ? PG_LLR_F64 : PG_LLR_F32);
     // Chunk = what one launch keeps resident.  A wave-sized launch runs all its warps in lockstep through the same phases of the
     // schedule (memory-heavy top layers, then leaf-heavy stretches), which costs the list kernel ~15 %; four quarter-grid launches on
     // four streams, offset by a quarter chunk each, interleave those phases and quarter the pipeline fill
@@ -535,27 +616,36 @@ static int decode_host(pg_ctx *ctx, const void *llr, int llr_is_f64, size_t B, u
     if (B > pc && !getenv("POLARGPU_NO_PIPELINE")) {
         int rc = ensure_pipe(ctx, pc, u_hat != nullptr);
         if (rc) return rc;
-        size_t i = 0;
-        for (size_t off = 0; off < B; off += pc, i++) {
-            const size_t b = std::min(pc, B - off);
-            const int s = (int)(i % nbuf), lane = (int)(i % lanes);
-            cudaStream_t cs = ctx->st_lane[lane];
-            if (i >= (size_t)nbuf) CU(cudaStreamWaitEvent(ctx->st_copy, ctx->ev_free[s], 0));
-            void *dst = conv ? ctx->p_in[s] : ctx->p_llr[s];
-            CU(cudaMemcpyAsync(dst, (const char *)llr + off * N * esz, b * N * esz, cudaMemcpyHostToDevice, ctx->st_copy));
-            CU(cudaEventRecord(ctx->ev_h2d[s], ctx->st_copy));
-            CU(cudaStreamWaitEvent(cs, ctx->ev_h2d[s], 0));
-            if (conv) { CU(launch_convert_llr(ctx->p_in[s], llr_is_f64 != 0, ctx->p_llr[s], ctx->f64, b * N, cs)); ctx->launches++; }
-            rc = run_decode_on(ctx, cs, lane_grid, lane * lane_grid, ctx->p_llr[s], b, nullptr, ctx->p_uhat[s], ctx->p_info[s], false);
-            if (rc) return rc;
-            if (u_hat) {
-                CU(launch_unpack_bits(ctx->p_uhat[s], ctx->p_bytes[s], b, (int)N, cs));
-                ctx->launches++;
-                CU(cudaMemcpyAsync(u_hat + off * N, ctx->p_bytes[s], b * N, cudaMemcpyDeviceToHost, cs));
+        auto enqueue_all = [&]() -> int {
+            size_t i = 0;
+            for (size_t off = 0; off < B; off += pc, i++) {
+                const size_t b = std::min(pc, B - off);
+                const int s = (int)(i % nbuf), lane = (int)(i % lanes);
+                cudaStream_t cs = ctx->st_lane[lane];
+                if (i >= (size_t)nbuf) CU(cudaStreamWaitEvent(ctx->st_copy, ctx->ev_free[s], 0));
+                void *dst = conv ? ctx->p_in[s] : ctx->p_llr[s];
+                CU(cudaMemcpyAsync(dst, (const char *)llr + off * N * esz, b * N * esz, cudaMemcpyHostToDevice, ctx->st_copy));
+                CU(cudaEventRecord(ctx->ev_h2d[s], ctx->st_copy));
+                CU(cudaStreamWaitEvent(cs, ctx->ev_h2d[s], 0));
+                if (conv) { CU(launch_convert_llr(ctx->p_in[s], llr_is_f64, ctx->p_llr[s], ctx->f64, b * N, cs)); ctx->launches++; }
+                int rc2 = run_decode_on(ctx, cs, lane_grid, lane * lane_grid, ctx->p_llr[s], b, nullptr, ctx->p_uhat[s], ctx->p_info[s], nullptr);
+                if (rc2) return rc2;
+                if (u_hat) {
+                    CU(launch_unpack_bits(ctx->p_uhat[s], ctx->p_bytes[s], b, (int)N, cs));
+                    ctx->launches++;
+                    CU(cudaMemcpyAsync(u_hat + off * N, ctx->p_bytes[s], b * N, cudaMemcpyDeviceToHost, cs));
+                }
+                if (u_hat_packed) CU(cudaMemcpyAsync(u_hat_packed + off * W, ctx->p_uhat[s], b * W * 4, cudaMemcpyDeviceToHost, cs));
+                if (flags) CU(cudaMemcpyAsync(flags + off, ctx->p_info[s], b * 4, cudaMemcpyDeviceToHost, cs));
+                CU(cudaEventRecord(ctx->ev_free[s], cs));
             }
-            if (u_hat_packed) CU(cudaMemcpyAsync(u_hat_packed + off * W, ctx->p_uhat[s], b * W * 4, cudaMemcpyDeviceToHost, cs));
-            if (flags) CU(cudaMemcpyAsync(flags + off, ctx->p_info[s], b * 4, cudaMemcpyDeviceToHost, cs));
-            CU(cudaEventRecord(ctx->ev_free[s], cs));
+            return PG_OK;
+        };
+        rc = enqueue_all();
+        if (rc) {  // copies and kernels of earlier chunks are still in flight and write into the caller's buffers: wait for them
+            cudaStreamSynchronize(ctx->st_copy);
+            for (int l = 0; l < lanes; l++) cudaStreamSynchronize(ctx->st_lane[l]);
+            return rc;
         }
         for (int l = 0; l < lanes; l++) CU(cudaStreamSynchronize(ctx->st_lane[l]));
     } else {
@@ -565,7 +655,7 @@ static int decode_host(pg_ctx *ctx, const void *llr, int llr_is_f64, size_t B, u
             if (rc) return rc;
             void *dst = conv ? ctx->d_in : ctx->d_llr;
             CU(cudaMemcpyAsync(dst, (const char *)llr + off * N * esz, b * N * esz, cudaMemcpyHostToDevice, ctx->st));
-            if (conv) { CU(launch_convert_llr(ctx->d_in, llr_is_f64 != 0, ctx->d_llr, ctx->f64, b * N, ctx->st)); ctx->launches++; }
+            if (conv) { CU(launch_convert_llr(ctx->d_in, llr_is_f64, ctx->d_llr, ctx->f64, b * N, ctx->st)); ctx->launches++; }
             rc = run_decode(ctx, ctx->d_llr, b, nullptr, ctx->d_uhat, ctx->d_info, false);
             if (rc) return rc;
             if (u_hat) {
@@ -596,11 +686,11 @@ extern "C" int pg_decode_llr_packed(pg_ctx *ctx, const void *llr, int llr_is_f64
 extern "C" int pg_decode_llr_counted(pg_ctx *ctx, const void *llr, int llr_is_f64, size_t B, const uint8_t *u_true, uint8_t *u_hat,
                                      pg_counters *acc, uint16_t *frame_err)
 {
-    if (!ctx || !llr || !u_true || !acc) return PG_ERR_ARG;
+    if (!ctx || !llr || !u_true || !acc || !llr_fmt_ok(llr_is_f64)) return PG_ERR_ARG;
     CU(cudaSetDevice(ctx->p.device));
     const size_t N = ctx->p.N, W = ctx->W;
-    const size_t esz = llr_is_f64 ? 8 : 4;
-    const bool conv = (llr_is_f64 != 0) != ctx->f64;
+    const size_t esz = llr_esz(llr_is_f64);
+    const bool conv = llr_is_f64 != (ctx->f64 ? PG_LLR_F64 : PG_LLR_F32);
     std::vector<uint32_t> packed;
     for (size_t off = 0; off < B; off += ctx->chunk_max) {
         const size_t b = std::min(ctx->chunk_max, B - off);
@@ -613,16 +703,16 @@ extern "C" int pg_decode_llr_counted(pg_ctx *ctx, const void *llr, int llr_is_f6
         CU(cudaMemcpyAsync(ctx->d_truth, packed.data(), b * W * 4, cudaMemcpyHostToDevice, ctx->st));
         void *dst = conv ? ctx->d_in : ctx->d_llr;
         CU(cudaMemcpyAsync(dst, (const char *)llr + off * N * esz, b * N * esz, cudaMemcpyHostToDevice, ctx->st));
-        if (conv) { CU(launch_convert_llr(ctx->d_in, llr_is_f64 != 0, ctx->d_llr, ctx->f64, b * N, ctx->st)); ctx->launches++; }
-        CU(cudaMemsetAsync(ctx->d_counters, 0, CNT_N * 8, ctx->st));
-        rc = run_decode(ctx, ctx->d_llr, b, ctx->d_truth, ctx->d_uhat, ctx->d_info, true);
+        if (conv) { CU(launch_convert_llr(ctx->d_in, llr_is_f64, ctx->d_llr, ctx->f64, b * N, ctx->st)); ctx->launches++; }
+        CU(cudaMemsetAsync(ctx->d_cnt2, 0, CNT_N * 8, ctx->st));
+        rc = run_decode_dev(ctx, ctx->d_llr, b, ctx->d_truth, ctx->d_uhat, ctx->d_info, ctx->d_cnt2);
         if (rc) return rc;
         if (u_hat) {
             CU(launch_unpack_bits(ctx->d_uhat, ctx->d_bytes, b, (int)N, ctx->st));
             ctx->launches++;
             CU(cudaMemcpyAsync(u_hat + off * N, ctx->d_bytes, b * N, cudaMemcpyDeviceToHost, ctx->st));
         }
-        CU(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, CNT_N * 8, cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaMemcpyAsync(ctx->h_counters, ctx->d_cnt2, CNT_N * 8, cudaMemcpyDeviceToHost, ctx->st));
         CU(cudaMemcpyAsync(ctx->h_info, ctx->d_info, b * 4, cudaMemcpyDeviceToHost, ctx->st));
         CU(cudaStreamSynchronize(ctx->st));
         add_counters(acc, ctx->h_counters);
@@ -659,12 +749,12 @@ static int simulate_chunk(pg_ctx *ctx, double ebn0_db, uint64_t first, size_t b,
 {
     int rc = ensure_capacity(ctx, b);
     if (rc) return rc;
-    CU(cudaMemsetAsync(ctx->d_counters, 0, CNT_N * 8, ctx->st));
+    CU(cudaMemsetAsync(ctx->d_cnt2, 0, CNT_N * 8, ctx->st));
     rc = run_channel(ctx, ebn0_db, first, b, true);
     if (rc) return rc;
-    rc = run_decode(ctx, ctx->d_llr, b, ctx->d_truth, nullptr, ctx->d_info, true);
+    rc = run_decode_dev(ctx, ctx->d_llr, b, ctx->d_truth, nullptr, ctx->d_info, ctx->d_cnt2);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, CNT_N * 8, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaMemcpyAsync(ctx->h_counters, ctx->d_cnt2, CNT_N * 8, cudaMemcpyDeviceToHost, ctx->st));
     if (want_info) CU(cudaMemcpyAsync(ctx->h_info, ctx->d_info, b * 4, cudaMemcpyDeviceToHost, ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
     return PG_OK;
@@ -704,6 +794,68 @@ static int exchange(pg_ctx *ctx, unsigned long long *host_vec, size_t count)
     return PG_OK;
 }
 
+// ring of round slots for pg_simulate: per-round counters, exchange matrix (device + pinned host), events; per-frame words on demand
+static int ensure_ring(pg_ctx *ctx, size_t frames, bool want_info)
+{
+    const size_t R = (size_t)ctx->p.nranks;
+    if (!ctx->st_comm) {
+        CU(cudaStreamCreateWithFlags(&ctx->st_comm, cudaStreamNonBlocking));
+        for (int r = 0; r < pg_ctx::kRing; r++) {
+            CU(cudaMalloc(&ctx->d_rc[r], CNT_N * 8));
+            CU(cudaMalloc(&ctx->d_xm[r], R * CNT_N * 8));
+            CU(cudaMallocHost(&ctx->h_xm[r], R * CNT_N * 8));
+            CU(cudaEventCreateWithFlags(&ctx->ev_round[r], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&ctx->ev_xdone[r], cudaEventDisableTiming));
+        }
+    }
+    if (want_info && frames > ctx->ring_cap) {
+        ctx->ring_cap = 0;
+        for (int r = 0; r < pg_ctx::kRing; r++) {
+            cudaFree(ctx->d_rinfo[r]);
+            ctx->d_rinfo[r] = nullptr;
+            CU(cudaMalloc(&ctx->d_rinfo[r], frames * 4));
+        }
+        ctx->ring_cap = frames;
+    }
+    return PG_OK;
+}
+
+// Enqueue one round into ring slot `slot`: channel + decode + count on the compute stream, then -- on the exchange stream, so that the
+// next round's kernels start right behind this round's -- the round's [nranks][CNT_N] matrix (own row = own counters), its NCCL
+// all-reduce when there is more than one rank, and the copy of the result into pinned host memory.  Nothing here waits for the GPU.
+static int enqueue_round(pg_ctx *ctx, int slot, double ebn0_db, uint64_t start, size_t mine, bool want_info)
+{
+    const int R = ctx->p.nranks, me = ctx->p.rank;
+    CU(cudaStreamWaitEvent(ctx->st, ctx->ev_xdone[slot], 0));  // the slot's previous round has left the device buffers
+    CU(cudaMemsetAsync(ctx->d_rc[slot], 0, CNT_N * 8, ctx->st));
+    if (mine) {
+        int rc = run_channel(ctx, ebn0_db, start, mine, true);
+        if (rc) return rc;
+        rc = run_decode_dev(ctx, ctx->d_llr, mine, ctx->d_truth, nullptr, want_info ? ctx->d_rinfo[slot] : nullptr, ctx->d_rc[slot]);
+        if (rc) return rc;
+    }
+    CU(cudaEventRecord(ctx->ev_round[slot], ctx->st));
+    CU(cudaStreamWaitEvent(ctx->st_comm, ctx->ev_round[slot], 0));
+    if (R > 1) {
+        CU(cudaMemsetAsync(ctx->d_xm[slot], 0, (size_t)R * CNT_N * 8, ctx->st_comm));
+        CU(cudaMemcpyAsync(ctx->d_xm[slot] + (size_t)me * CNT_N, ctx->d_rc[slot], CNT_N * 8, cudaMemcpyDeviceToDevice, ctx->st_comm));
+        ncclResult_t r = g_nccl.AllReduce(ctx->d_xm[slot], ctx->d_xm[slot], (size_t)R * CNT_N, ncclUint64, ncclSum, ctx->comm, ctx->st_comm);
+        if (r != ncclSuccess) { ctx->err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"); return PG_ERR_NCCL; }
+        ctx->sim_allreduces++;
+        CU(cudaMemcpyAsync(ctx->h_xm[slot], ctx->d_xm[slot], (size_t)R * CNT_N * 8, cudaMemcpyDeviceToHost, ctx->st_comm));
+    } else {
+        CU(cudaMemcpyAsync(ctx->h_xm[slot], ctx->d_rc[slot], CNT_N * 8, cudaMemcpyDeviceToHost, ctx->st_comm));
+    }
+    CU(cudaEventRecord(ctx->ev_xdone[slot], ctx->st_comm));
+    ctx->sim_rounds++;
+    return PG_OK;
+}
+
+// The Monte-Carlo loop of the reference's main() (SC_128.c:164-222), pipelined: round i+1 is enqueued before the host looks at round
+// i, so the GPU never waits for the host or for the collective.  A run that overshoots its stopping condition by the one round in
+// flight discards that round: the result is defined by global frame order (SC_128.c:169), not by what was computed.
+// With a frame budget only (target_err_blocks == 0) the number of rounds is known in advance: the counters accumulate on the
+// device over all rounds and ONE all-reduce combines the ranks at the end.
 extern "C" int pg_simulate(pg_ctx *ctx, double ebn0_db, uint64_t first_frame, uint64_t target_err_blocks, uint64_t max_frames,
                            int exact_stop, pg_counters *out)
 {
@@ -712,40 +864,125 @@ extern "C" int pg_simulate(pg_ctx *ctx, double ebn0_db, uint64_t first_frame, ui
     const int R = ctx->p.nranks, me = ctx->p.rank;
     static_assert(sizeof(pg_counters) == CNT_N * 8, "pg_counters layout");
     std::memset(out, 0, sizeof(*out));
+    if (R > 1 && !ctx->comm) { ctx->err = "nranks > 1 but pg_comm_init was not called"; return PG_ERR_NCCL; }
+    ctx->sim_rounds = ctx->sim_allreduces = 0;
     uint64_t next = first_frame;  // first global frame of the next round
+
+    if (target_err_blocks == 0) {
+        // ---- frame budget only: fixed schedule, device-side accumulation, one exchange
+        int rc = ensure_capacity(ctx, std::min<uint64_t>(ctx->chunk_max, (max_frames + R - 1) / R));
+        if (rc) return rc;
+        CU(cudaMemsetAsync(ctx->d_cnt2, 0, CNT_N * 8, ctx->st));
+        uint64_t left = max_frames;
+        unsigned queued = 0;
+        while (left) {
+            const size_t chunk = (size_t)std::min<uint64_t>(ctx->chunk_max, (left + R - 1) / R);  // the last round splits what is left
+            uint64_t start = 0, mine = 0;
+            pg_partition(next, chunk, R, me, left, &start, &mine);
+            if (mine) {
+                rc = run_channel(ctx, ebn0_db, start, (size_t)mine, true);
+                if (rc) return rc;
+                rc = run_decode_dev(ctx, ctx->d_llr, (size_t)mine, ctx->d_truth, nullptr, nullptr, ctx->d_cnt2);
+                if (rc) return rc;
+            }
+            ctx->sim_rounds++;
+            const uint64_t round = std::min<uint64_t>(left, (uint64_t)R * chunk);
+            left -= round;
+            next += round;
+            if ((++queued & 63u) == 0) CU(cudaStreamSynchronize(ctx->st));  // bound the launch queue
+        }
+        CU(cudaMemcpyAsync(ctx->h_counters, ctx->d_cnt2, CNT_N * 8, cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaStreamSynchronize(ctx->st));
+        std::memcpy(out, ctx->h_counters, CNT_N * 8);
+        if (R > 1) ctx->sim_allreduces++;
+        return exchange(ctx, reinterpret_cast<unsigned long long *>(out), CNT_N);
+    }
+
+    // ---- error target (with or without a frame budget): rounds of nranks x chunk frames, chunk doubling from 4096
+    struct Round { uint64_t first; size_t chunk; uint64_t mine; uint64_t round_frames; };
+    Round ring[pg_ctx::kRing];
     size_t chunk = std::min<size_t>(ctx->chunk_max, 4096);
+    {
+        int rc = ensure_capacity(ctx, ctx->chunk_max);
+        if (!rc) rc = ensure_ring(ctx, ctx->chunk_max, exact_stop != 0);
+        if (rc) return rc;
+    }
+    uint64_t planned = 0;          // frames of all rounds enqueued so far
+    unsigned head = 0, tail = 0;   // rounds enqueued / rounds merged
+    auto enqueue_next = [&]() -> int {
+        const uint64_t budget = max_frames ? (max_frames - planned) : ~0ull;
+        Round rd;
+        rd.first = next; rd.chunk = chunk;
+        uint64_t start = 0;
+        pg_partition(next, chunk, R, me, budget, &start, &rd.mine);
+        rd.round_frames = std::min<uint64_t>(budget, (uint64_t)R * chunk);
+        const int slot = (int)(head % pg_ctx::kRing);
+        int rc = enqueue_round(ctx, slot, ebn0_db, start, (size_t)rd.mine, exact_stop != 0);
+        if (rc) return rc;
+        ring[slot] = rd;
+        head++;
+        planned += rd.round_frames;
+        next += (uint64_t)R * chunk;
+        if (chunk < ctx->chunk_max) chunk = std::min(ctx->chunk_max, chunk * 2);
+        return PG_OK;
+    };
+    auto drain = [&]() {  // rounds in flight past the stopping point: let them finish (every rank enqueued the same ones)
+        cudaStreamSynchronize(ctx->st);
+        cudaStreamSynchronize(ctx->st_comm);
+    };
+    // the BPR statistic sums on the device over everything that was decoded: no round may run past the stopping point then
+    const unsigned depth = ctx->bpr_ns ? 1u : 2u;
+    int rc = enqueue_next();
+    if (rc) return rc;
     std::vector<pg_counters> xc((size_t)R);
     while (true) {
-        const uint64_t budget = max_frames ? (max_frames - out->frames) : ~0ull;
-        if (max_frames && budget == 0) break;
-        uint64_t start = 0, mine = 0;
-        pg_partition(next, chunk, R, me, budget, &start, &mine);
-        std::memset(xc.data(), 0, sizeof(pg_counters) * xc.size());
-        if (mine) {
-            int rc = simulate_chunk(ctx, ebn0_db, start, (size_t)mine, exact_stop != 0);
-            if (rc) return rc;
-            std::memcpy(&xc[me], ctx->h_counters, CNT_N * 8);
+        // keep one more round in flight while the host waits for the oldest one
+        if (head - tail < depth && (!max_frames || planned < max_frames)) {
+            rc = enqueue_next();
+            if (rc) { drain(); return rc; }
         }
-        int rc = exchange(ctx, reinterpret_cast<unsigned long long *>(xc.data()), xc.size() * CNT_N);
-        if (rc) return rc;
+        const int slot = (int)(tail % pg_ctx::kRing);
+        CU(cudaEventSynchronize(ctx->ev_xdone[slot]));
+        std::memset(xc.data(), 0, sizeof(pg_counters) * xc.size());
+        if (R > 1) std::memcpy(xc.data(), ctx->h_xm[slot], (size_t)R * CNT_N * 8);
+        else std::memcpy(&xc[0], ctx->h_xm[slot], CNT_N * 8);
         int cut = -1;
         uint64_t need = 0;
         pg_merge_round(xc.data(), R, target_err_blocks, exact_stop, out, &cut, &need);
+        bool done = false;
         if (cut >= 0) {
             // the target-th block error fell into rank `cut`'s chunk: that rank truncates, everybody learns the result
             pg_counters part;
             std::memset(&part, 0, sizeof(part));
-            if (cut == me) pg_truncate_info(ctx->h_info, (size_t)mine, need, &part);
+            drain();
+            if (cut == me) {
+                rc = ensure_capacity(ctx, (size_t)ring[slot].mine);
+                if (rc) return rc;
+                CU(cudaMemcpy(ctx->h_info, ctx->d_rinfo[slot], (size_t)ring[slot].mine * 4, cudaMemcpyDeviceToHost));
+                pg_truncate_info(ctx->h_info, (size_t)ring[slot].mine, need, &part);
+            }
             rc = exchange(ctx, reinterpret_cast<unsigned long long *>(&part), CNT_N);
             if (rc) return rc;
+            if (R > 1) ctx->sim_allreduces++;
             add_counters(out, reinterpret_cast<unsigned long long *>(&part));
-            break;
+            return PG_OK;
         }
-        if (target_err_blocks && out->err_blocks >= target_err_blocks) break;
-        if (max_frames && out->frames >= max_frames) break;
-        next += (uint64_t)R * chunk;
-        if (chunk < ctx->chunk_max) chunk = std::min(ctx->chunk_max, chunk * 2);
+        tail++;
+        if (out->err_blocks >= target_err_blocks) done = true;
+        if (max_frames && out->frames >= max_frames) done = true;
+        if (done) { drain(); return PG_OK; }
+        if (tail == head) {  // nothing in flight and not done (frame budget exhausted exactly would have ended above)
+            rc = enqueue_next();
+            if (rc) return rc;
+        }
     }
+}
+
+extern "C" int pg_simulate_stats(const pg_ctx *ctx, uint64_t *rounds, uint64_t *allreduces)
+{
+    if (!ctx) return PG_ERR_ARG;
+    if (rounds) *rounds = ctx->sim_rounds;
+    if (allreduces) *allreduces = ctx->sim_allreduces;
     return PG_OK;
 }
 

@@ -13,6 +13,8 @@
 // Encoding is the n-stage butterfly on packed words (5 in-register stages + shuffles).  LLRs are written as
 // 16-byte vectors, 512 contiguous bytes per warp instruction; the truth vector u is written packed.
 #include "engine.h"
+#include <cuda_fp16.h>
+#include <algorithm>
 #include "polar_common.cuh"
 
 namespace polar {
@@ -189,15 +191,39 @@ __global__ void convert_kernel(const S *__restrict__ s, D *__restrict__ d, size_
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) d[i] = (D)s[i];
 }
 
-cudaError_t launch_convert_llr(const void *src, bool src_f64, void *dst, bool dst_f64, size_t count, cudaStream_t st)
+// packed-half LLRs (PG_LLR_F16: half the host-to-device bytes of a streamed frame) to the decoder's arithmetic type, 8 values per thread step
+template <typename D>
+__global__ void convert_h_kernel(const uint4 *__restrict__ s, D *__restrict__ d, size_t n8, const __half *__restrict__ tail_s, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = s[i];
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&w[e]));
+            d[i * 8 + 2 * e] = (D)f.x;
+            d[i * 8 + 2 * e + 1] = (D)f.y;
+        }
+    }
+    if (blockIdx.x == 0)
+        for (size_t i = n8 * 8 + threadIdx.x; i < n; i += blockDim.x) d[i] = (D)__half2float(tail_s[i]);
+}
+
+// src_fmt: 0 float, 1 double, 2 half (include/polargpu.h PG_LLR_*)
+cudaError_t launch_convert_llr(const void *src, int src_fmt, void *dst, bool dst_f64, size_t count, cudaStream_t st)
 {
     if (count == 0) return cudaSuccess;
     const int threads = 256;
     size_t blocks = (count + threads - 1) / threads;
     if (blocks > 148 * 32) blocks = 148 * 32;
-    if (src_f64 && !dst_f64) convert_kernel<double, float><<<(unsigned)blocks, threads, 0, st>>>((const double *)src, (float *)dst, count);
-    else if (!src_f64 && dst_f64) convert_kernel<float, double><<<(unsigned)blocks, threads, 0, st>>>((const float *)src, (double *)dst, count);
-    else return cudaErrorInvalidValue;
+    if (src_fmt == 1 && !dst_f64) convert_kernel<double, float><<<(unsigned)blocks, threads, 0, st>>>((const double *)src, (float *)dst, count);
+    else if (src_fmt == 0 && dst_f64) convert_kernel<float, double><<<(unsigned)blocks, threads, 0, st>>>((const float *)src, (double *)dst, count);
+    else if (src_fmt == 2) {
+        const size_t n8 = count / 8;
+        blocks = std::max<size_t>(1, std::min<size_t>((n8 + threads - 1) / threads, 148 * 16));
+        if (dst_f64) convert_h_kernel<double><<<(unsigned)blocks, threads, 0, st>>>((const uint4 *)src, (double *)dst, n8, (const __half *)src, count);
+        else convert_h_kernel<float><<<(unsigned)blocks, threads, 0, st>>>((const uint4 *)src, (float *)dst, n8, (const __half *)src, count);
+    } else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }
 

@@ -6,7 +6,9 @@
 #include "../../include/polargpu.h"
 
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
+#include <vector>
 
 extern "C" int pg_partition(uint64_t round_first, uint64_t chunk, int nranks, int rank, uint64_t budget,
                             uint64_t *start, uint64_t *count)
@@ -54,5 +56,46 @@ extern "C" int pg_merge_round(const pg_counters *round, int nranks, uint64_t tar
         }
         add(acc, &round[q]);
     }
+    return PG_OK;
+}
+
+// CRC parity table in the reference's file format (/root/reference/CRC_6.dat: K rows of r integers 0/1, row i = coefficients
+// c0..c(r-1) of D^(r+i) mod g(D), i.e. row i of the systematic generator Gc that CASCL_1024_sys.c:49-561 spells out as a literal;
+// UTF-16 with a byte-order mark as the author's editor saved it, or plain ASCII; blanks, CR/LF free-form).
+// Row 0 is D^r mod g(D) = g(D) - D^r, so the file determines the polynomial; every further row must be D times its predecessor
+// modulo g(D), otherwise the file is not a CRC table and the call fails.
+extern "C" int pg_crc_table_load(const char *path, int K, int r, uint64_t *crc_poly, uint32_t *rows)
+{
+    if (!path || K < 1 || r < 1 || r > 32 || !crc_poly) return PG_ERR_ARG;
+    FILE *f = std::fopen(path, "rb");
+    if (!f) return PG_ERR_ARG;
+    std::vector<unsigned char> raw;
+    unsigned char buf[4096];
+    size_t got;
+    while ((got = std::fread(buf, 1, sizeof(buf), f)) > 0) raw.insert(raw.end(), buf, buf + got);
+    std::fclose(f);
+    std::vector<int> v;
+    const bool le = raw.size() >= 2 && raw[0] == 0xFF && raw[1] == 0xFE, be = raw.size() >= 2 && raw[0] == 0xFE && raw[1] == 0xFF;
+    const size_t step = (le || be) ? 2 : 1;
+    for (size_t i = (le || be) ? 2 : 0; i + step <= raw.size(); i += step) {
+        const unsigned ch = (step == 1) ? raw[i] : (le ? (raw[i] | (raw[i + 1] << 8)) : (raw[i + 1] | (raw[i] << 8)));
+        if (ch == '0' || ch == '1') v.push_back((int)(ch - '0'));
+        else if (ch != ' ' && ch != '\t' && ch != '\r' && ch != '\n' && ch != 0xFEFF) return PG_ERR_ARG;
+    }
+    if (v.size() != (size_t)K * (size_t)r) return PG_ERR_ARG;
+    std::vector<uint32_t> w((size_t)K, 0u);
+    for (int i = 0; i < K; i++)
+        for (int b = 0; b < r; b++)
+            if (v[(size_t)i * r + b]) w[i] |= 1u << b;
+    const uint64_t low = w[0], mask = (r == 32) ? 0xFFFFFFFFull : ((1ull << r) - 1ull);
+    if (!(low & 1ull)) return PG_ERR_ARG;  // g(D) must contain the constant term
+    uint64_t cur = low;
+    for (int i = 1; i < K; i++) {
+        cur <<= 1;
+        if ((cur >> r) & 1ull) cur = (cur & mask) ^ low;
+        if ((uint32_t)cur != w[i]) return PG_ERR_ARG;
+    }
+    *crc_poly = low | (1ull << r);
+    if (rows) std::memcpy(rows, w.data(), sizeof(uint32_t) * (size_t)K);
     return PG_OK;
 }

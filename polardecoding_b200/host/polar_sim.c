@@ -50,7 +50,7 @@ typedef struct prog_def {
     int fmt;             /* output format id */
 } prog_def;
 
-enum { F_SC, F_SCL_1E1, F_SCL_1E2, F_SCL_FAG, F_CASCL_1E3, F_CASCL_1E4, F_CASCL_SYS, F_BP_128, F_BP_1024, F_BPR };
+enum { F_SC, F_SCL_1E1, F_SCL_1E2, F_SCL_FAG, F_CASCL_1E3, F_CASCL_1E4, F_CASCL_SYS, F_CASCL_128_SYS, F_BP_128, F_BP_1024, F_BPR };
 
 static const prog_def PROGS[] = {
     {"SC_128", 1.0, 4.0, 100, 0, F_SC},           /* SC_128.c:164,169,218-221 */
@@ -62,6 +62,7 @@ static const prog_def PROGS[] = {
     {"CASCL_128", 1.0, 3.0, 200, 10000, F_CASCL_1E3},   /* CASCL_128.c:124,194,257 */
     {"CASCL_1024_L8", 1.0, 1.5, 200, 10000, F_CASCL_1E4}, /* CASCL_1024_L8.c:164,234,308 */
     {"CASCL_1024_sys", 2.5, 2.5, 200, 10000, F_CASCL_SYS}, /* CASCL_1024_sys.c:681,765,832-835 */
+    {"CASCL_128_sys", 1.0, 3.5, 200, 10000, F_CASCL_128_SYS}, /* systematic CRC-6 (CRC_6.dat); sweep and line format of result_128_fag/CAL8_0.dat */
     {"BP_128", 1.0, 4.0, 200, 1000, F_BP_128},    /* BP_128.c:96,163,217 */
     {"BP_1024", 1.0, 3.5, 200, 1000, F_BP_1024},  /* BP_1024.c:136,203,255-257 */
     {"BP_128_fag", 1.0, 4.0, 200, 1000, F_BP_128}, /* BP_128_fag.c:98,179 */
@@ -152,6 +153,10 @@ static void print_point(const prog_def *pd, const pg_params *p, double snr, cons
         break;
     case F_CASCL_SYS:
         printf("bSNR = %.2lf\trun = %d\tBLER = %lfe-3\t", snr, run, ((double)errBlock) / (run / 1000.0));
+        printf("Error bit = %d\tBER = %lfe-3\n", errbit, ((double)errbit) / (K) / (run / 1000.0));
+        break;
+    case F_CASCL_128_SYS: /* result_128_fag/CAL8_0.dat */
+        printf("L = %d\tbSNR = %.2lf\terror block = %d\trun = %d\tBLER = %lfe-3\n", L, snr, errBlock, run, ((double)errBlock) / (run / 1000.0));
         printf("Error bit = %d\tBER = %lfe-3\n", errbit, ((double)errbit) / (K) / (run / 1000.0));
         break;
     case F_BP_128:
@@ -310,6 +315,7 @@ int main(int argc, char **argv)
     long ble = -1, L = -1, iters = -1, gpus = 1;
     long long seed = -1, maxf = 0;
     int use_ref = 0, real = -1, early = 0, verbose = 0;
+    const char *crc_file = NULL;
     if (!name[0]) { const char *b = strrchr(argv[0], '/'); name = b ? b + 1 : argv[0]; }
     for (int i = 1; i < argc; i++) {
         const char *a = argv[i], *v = (i + 1 < argc) ? argv[i + 1] : NULL;
@@ -326,6 +332,7 @@ int main(int argc, char **argv)
         else if (!strcmp(a, "--L") && v) { L = atol(v); i++; }
         else if (!strcmp(a, "--iters") && v) { iters = atol(v); i++; }
         else if (!strcmp(a, "--gpus") && v) { gpus = atol(v); i++; }
+        else if (!strcmp(a, "--crc-file") && v) { crc_file = v; i++; }
         else if (!strcmp(a, "--early-stop")) early |= 1;
         else if (!strcmp(a, "--gmatrix-stop")) early |= 2;
         else if (!strcmp(a, "--verbose")) verbose = 1;
@@ -340,6 +347,14 @@ int main(int argc, char **argv)
     if (pg_params_preset(&p, pd->name)) { fprintf(stderr, "polar_sim: no preset for %s\n", pd->name); return 2; }
     if (L > 0) p.list_size = (int)L;
     if (iters > 0) p.iter_max = (int)iters;
+    if (crc_file) { /* the CRC parity table in the reference's file format (CRC_6.dat): it determines g(D) */
+        uint64_t poly = 0;
+        if (p.crc_bits == 0 || pg_crc_table_load(crc_file, p.K, p.crc_bits, &poly, NULL)) {
+            fprintf(stderr, "polar_sim: %s is not a %d x %d CRC parity table\n", crc_file, p.K, p.crc_bits);
+            return 2;
+        }
+        p.crc_poly = poly;
+    }
     p.bp_early_stop = early;
     p.real = (real >= 0) ? real : (use_ref ? PG_REAL_F64 : PG_REAL_F32);
     if (e0 < 0) { e0 = pd->e0; e1 = pd->e1; }

@@ -60,3 +60,55 @@ def test_bpr128_reproduces_reference_stdout():
     assert out == KAT["K_BPr_128"]["stdout"]
     out = run("BPr_128", "--ebn0", "2.0", "--ble", "50", "--seed", "3")
     assert "After 80 iterations:" in out and "K * BER" in out
+
+
+# ---- round 2: every list size of the author's captures, K3, and the print formats of the remaining programs -----------------
+FIRST = json.load(open(os.path.join(ROOT, "tests", "golden", "kat_firstlines.json")))
+
+
+def capture_blocks(text):
+    """{L: [line, ...]} of a capture that holds one block of result lines per list size"""
+    import re
+    blocks = {}
+    for line in text.replace("\r", "").split("\n"):
+        m = re.match(r"L = (\d+)\tbSNR = ", line)
+        if m:
+            blocks.setdefault(int(m.group(1)), []).append(line)
+    return blocks
+
+
+@pytest.mark.parametrize("L", [2, 4, 16, 32])
+def test_scl128_capture_every_list_size(L):
+    """myResult_128/SCL128out_errblock50.dat: SCL_128.c with `#define L` edited per run (SCL_128.c:16), SEED = 1024, six points"""
+    want = capture_blocks(KAT["captures"]["myResult_128/SCL128out_errblock50.dat"])[L]
+    assert len(want) == 6
+    out = run("SCL_128", "--rng", "ref", "--L", str(L), "--ebn0", "1.0:0.5:3.5")
+    assert out == "".join(l + "\n" for l in want)
+
+
+@pytest.mark.parametrize("L,points", [(8, 5), (2, 4), (4, 4), (16, 4), (32, 3)])
+def test_scl1024_capture_k3(L, points):
+    """K3 = myResult_1024/SCL1024out.dat (SEED = 1024): run = 227, 1026, 5867, 21575, 178842 for L = 8 -- all five points -- and the
+    first points of the other four list sizes (L = 16 / 32 at N = 1024: the 64-bit pointer word, one or two frames per warp)"""
+    want = capture_blocks(FIRST["capture_SCL1024out"])[L][:points]
+    if L == 8:
+        assert [int(l.split("run = ")[1].split()[0]) for l in want] == [227, 1026, 5867, 21575, 178842]
+    out = run("SCL_1024", "--rng", "ref", "--L", str(L), "--ebn0", "1.0:0.5:%.1f" % (1.0 + 0.5 * (points - 1)))
+    assert out == "".join(l + "\n" for l in want)
+
+
+@pytest.mark.parametrize("prog", ["SC_1024", "SC_128_fag", "SCL_1024", "SCL_128_fag", "BP_128", "BP_128_fag", "BP_1024", "CASCL_1024_sys"])
+def test_first_lines_equal_the_compiled_reference(prog):
+    """print formats of the programs not covered above (e.g. BP_1024.c:255-257, CASCL_1024_sys.c:832-835, SCL_128_fag.c:256-259): the
+    first stdout lines of the compiled reference (tools/make_kat_firstlines.py) against the drop-in program with the same seed"""
+    import re
+    k = FIRST[prog]
+    want = k["stdout"]
+    snrs = [float(x) for x in re.findall(r"bSNR = ([0-9.]+)", want)]
+    assert snrs, "golden has no result line"
+    args = ["--rng", "ref", "--seed", str(k["seed"]), "--ebn0", "%.1f:0.5:%.1f" % (snrs[0], snrs[-1])]
+    if "ble" in k:
+        args += ["--ble", str(k["ble"])]
+    out = run(prog, *args)
+    n = len(want.splitlines())
+    assert "".join(l + "\n" for l in out.splitlines()[:n]) == want

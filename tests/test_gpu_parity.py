@@ -3,6 +3,8 @@
 
 Bar (BASELINE.json north_star): hard decisions bit-exact for the fp64 instantiation; for fp32 the frames whose
 decisions differ are counted and must stay rare (SC: none expected; CA-SCL: < 1e-3 of frames at low SNR)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -77,12 +79,10 @@ def test_fp32_flip_rate(prog, B, ebn0):
     fer_o = float((want != u).any(1).mean())
     fer_g = float((got != u).any(1).mean())
     print("%s fp32: %d/%d frames differ from fp64 oracle; FER oracle %.4f gpu %.4f; tie frames %d" % (prog, diff, B, fer_o, fer_g, int((flags & 1).sum())))
-    if o.kind() == "sc":
-        assert diff == 0
-    elif o.kind() in ("scl", "cascl"):
-        assert diff <= max(1, B // 50)
-    else:  # BP is chaotic under the discontinuous table: only the error rate is comparable
-        assert abs(fer_o - fer_g) <= 0.15
+    if o.kind() in ("sc", "scl", "cascl"):
+        assert diff == 0          # fixed seeds: exact expectation (the rate over millions of frames is tested below)
+    else:  # BP is chaotic under the discontinuous table: only the error rate is comparable -- at most one frame apart here
+        assert abs(fer_o - fer_g) * B <= 1.0
     eng.close()
 
 
@@ -175,22 +175,21 @@ def test_pipelined_host_path_equals_single_chunk():
     eng.close()
 
 
-def test_fp32_flip_rate_is_below_the_north_star_bar():
-    """BASELINE.json north_star: fp32 flips (near-zero LLR / path-metric ties) must stay below 1e-4 of frames.  Both modes
-    on the GPU on identical float-representable LLRs; the fp64 mode is bit-exact with the reference (tests above).
-    profiles/r1_fp32_flip_rate.md has the 200 000-frame table (CA-SCL 1024: 7e-5 at 1.0 dB, 3.5e-5 at 1.5 dB, 0 at >= 2 dB)."""
-    from polardecoding_b200 import Engine
-    e32 = Engine("CASCL_1024_L8", real="f32", seed=99, data_mode=1)
-    e64 = Engine("CASCL_1024_L8", real="f64", seed=99, data_mode=1)
-    B, diff = 60000, 0
-    for off in range(0, B, 20000):
-        llr, _ = e32.channel(1.5, off, 20000)
-        d32, _ = e32.decode_llr(llr, packed=True)
-        d64, _ = e64.decode_llr(llr, packed=True)
-        diff += int((d32 != d64).any(1).sum())
-    print("CA-SCL 1024 L=8 at 1.5 dB: %d of %d frames differ between fp32 and fp64" % (diff, B))
-    assert diff <= 12          # 1e-4 of 60 000 = 6 expected at the bar; measured ~2; allow Poisson spread
-    e32.close(); e64.close()
+@pytest.mark.parametrize("prog,ebn0,frames", [("CASCL_1024_L8", 1.0, 4000000), ("CASCL_1024_L8", 1.5, 2000000), ("CASCL_1024_L8", 2.0, 2000000),
+                                              ("SCL_1024", 1.0, 2000000)])
+def test_fp32_flip_rate_is_below_the_north_star_bar(prog, ebn0, frames):
+    """BASELINE.json north_star: fp32 flips (near-zero LLR / path-metric ties) must stay below 1e-4 of frames.  Millions of
+    device-resident frames (Philox channel -> both decode kernels -> decisions compared on the device), fp32 against the fp64
+    instantiation, which is bit-exact with the reference (tests above).  The assertion is the one-sided 95 % upper confidence
+    bound of the rate, not the point estimate.  Measured (profiles/r2_fp32_flip_rate.md): CA-SCL 1024 L=8 361 of 4e6 at 1.0 dB
+    (bound 9.9e-5), 47 of 4e6 at 1.5 dB, 0 of 4e6 at the bench's 2.0 dB."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from flip_rate_dev import flips, upper95
+    n, d, t = flips(prog, ebn0, frames)
+    ub = upper95(d, n)
+    print("%s at %.1f dB: %d of %d frames differ between fp32 and fp64 (rate %.2e, 95 %% upper bound %.2e; %d tie-flagged)" % (prog, ebn0, d, n, d / n, ub, t))
+    assert n == frames and ub < 1e-4
 
 
 @pytest.mark.parametrize("prog,B,ebn0", [("BP_1024", 4096, 2.5), ("BP_128", 20000, 3.0)])
@@ -291,4 +290,110 @@ def test_device_frame_info_matches_host_flags(prog, ebn0, over):
     assert ((w & 0xFFFF) == 0).all()                                  # no truth vector: no error count
     assert ((((w >> 16) & 3) | ((w >> 24) << 8)) == flags).all()      # PG_INFO_TO_FLAGS
     assert flags.any(), "the case should exercise at least one flag"
+    eng.close()
+
+
+# ---- round 2: list sizes 16 / 32 at N = 1024, the systematic CRC-6 variant, FER points of the author's deepest captures ---------
+def _golden_first():
+    import json
+    return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kat_firstlines.json")))
+
+
+def _pooled(rows, snr, L=None):
+    """(block errors, frames) of a capture's seeds pooled at one Eb/N0 point"""
+    c = [r for r in rows if abs(r["snr"] - snr) < 1e-9 and r["err"] and (L is None or r["L"] in (None, L))]
+    return sum(r["err"] for r in c), sum(r["run"] for r in c)
+
+
+@pytest.mark.parametrize("prog,L,B,ebn0", [("CASCL_1024_L8", 16, 24, 1.0), ("CASCL_1024_L8", 32, 12, 1.0), ("SCL_1024", 32, 8, 1.5), ("SCL_1024", 16, 10, 1.0),
+                                           ("CASCL_1024_L8", 2, 32, 1.5), ("CASCL_1024_L8", 4, 32, 1.5), ("CASCL_1024_sys", 32, 8, 1.0)])
+def test_other_list_sizes_n1024(prog, L, B, ebn0):
+    """L = 16 and 32 at N = 1024 (two frames / one frame per warp, the 64-bit pointer word for L = 32): fp64 against the oracle"""
+    from polardecoding_b200 import Engine
+    o = Oracle(prog)
+    u, llr = frames(o, B, ebn0, seed=31 + L)
+    want, aux = o.decode(llr, L=L)
+    eng = Engine(prog, real="f64", list_size=L)
+    got, flags = eng.decode_llr(llr)
+    assert (got == want).all(), describe(got, want, flags)
+    assert ((flags & 3) == (aux & 3)).all()
+    eng.close()
+
+
+def test_cascl1024_l32_fer_matches_the_authors_capture():
+    """myResult_1024/CASCL_L32.dat (the author's deepest list size): pooled BLER at 2.0 dB against 8e5 frames of the fp32 kernel"""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from results import parse
+    from polardecoding_b200 import Engine
+    e_ref, n_ref = _pooled(parse(_golden_first()["capture_CASCL_L32"]), 2.0, 32)
+    assert e_ref >= 300
+    eng = Engine("CASCL_1024_L8", real="f32", list_size=32, seed=77)
+    acc, _ = eng.simulate_batch(2.0, 0, 800000)
+    p_ref, p = e_ref / n_ref, acc.err_blocks / acc.frames
+    z = (p - p_ref) / (p_ref * np.sqrt(1.0 / e_ref + 1.0 / max(1, acc.err_blocks)))
+    print("CA-SCL 1024 L=32 at 2.0 dB: reference %.3e (%d errors), GPU %.3e (%d errors of %d), z = %+.2f; %.2f M frames/s"
+          % (p_ref, e_ref, p, acc.err_blocks, acc.frames, z, acc.frames / eng.last_kernel_ms()[0] / 1e3))
+    assert abs(z) < 2.6
+    eng.close()
+
+
+def test_systematic_crc6_variant():
+    """the systematic CRC-6 CA-SCL at N = 128 whose parity table is the reference's CRC_6.dat and whose results are
+    result_128_fag/CAL8_0.dat: (1) the table file gives the engine's polynomial, (2) fp64 decisions equal the oracle's for the same
+    code, (3) the block error rate at 2.0 and 2.5 dB lies within the 95 % interval of the author's pooled seeds."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from results import parse
+    from polardecoding_b200 import Engine
+    from polardecoding_b200.capi import preset
+    p = preset("CASCL_128_sys")
+    assert (p.N, p.K, p.crc_bits, p.crc_poly, p.crc_systematic, p.list_size, p.count_from) == (128, 64, 6, 0x61, 1, 8, 6)
+    o = Oracle(N=128, K=64, r=6, crc_poly=0x61, crc_systematic=1, L=8)
+    eng = Engine("CASCL_128_sys", real="f64", seed=5, data_mode=1)
+    llr, u = eng.channel(1.5, 0, 300)
+    for f in range(3):   # the channel kernel's frames are systematic CRC code words
+        import ctypes as C
+        cw = np.ascontiguousarray(u[f, o.I], dtype=np.int32)
+        assert o.lib.po_crc_check(C.byref(o.code), cw.ctypes.data_as(C.POINTER(C.c_int))) == 1
+    want, aux = o.decode(llr, kind="cascl", L=8)
+    got, flags = eng.decode_llr(llr)
+    assert (got == want).all(), describe(got, want, flags)
+    eng.close()
+    rows = parse(_golden_first()["capture_CAL8_0"])
+    eng = Engine("CASCL_128_sys", real="f32", seed=9)
+    for snr, B in ((2.0, 200000), (2.5, 400000)):
+        e_ref, n_ref = _pooled(rows, snr, 8)
+        acc, _ = eng.simulate_batch(snr, 0, B)
+        p_ref, pg = e_ref / n_ref, acc.err_blocks / acc.frames
+        z = (pg - p_ref) / (p_ref * np.sqrt(1.0 / e_ref + 1.0 / max(1, acc.err_blocks)))
+        print("CASCL_128_sys at %.1f dB: CAL8_0.dat %.4e (%d errors), GPU %.4e (%d errors), z = %+.2f" % (snr, p_ref, e_ref, pg, acc.err_blocks, z))
+        assert e_ref >= 400 and abs(z) < 2.6
+    eng.close()
+
+
+@pytest.mark.parametrize("prog,ebn0,B", [("CASCL_1024_L8", 1.5, 60000), ("BP_1024", 2.5, 6000), ("SC_128", 2.0, 100000)])
+def test_fp16_llr_input(prog, ebn0, B):
+    """PG_LLR_F16 (optional input format, half the host-to-device bytes): the LLRs a host hands over are rounded to binary16, so --
+    like PG_REAL_H2 -- it is judged on FER: the same frames through float32 and float16 buffers, block error rates within the 95 %
+    interval of each other; and the conversion itself is exact: float16 input equals float32 input that holds the same rounded values."""
+    from polardecoding_b200 import Engine
+    eng = Engine(prog, real="f32", seed=21, data_mode=1)
+    llr, u = eng.channel(ebn0, 0, B)
+    h = llr.astype(np.float16)
+    d32, _ = eng.decode_llr(llr, packed=True)
+    d16, _ = eng.decode_llr(h, packed=True)
+    dq, _ = eng.decode_llr(h.astype(np.float32), packed=True)
+    assert (d16 == dq).all()
+    up = np.packbits(u, axis=1, bitorder="little").view(np.uint32)
+    m = np.packbits(eng.inI[None, :], axis=1, bitorder="little").view(np.uint32)
+    e32 = int((((d32 ^ up) & m) != 0).any(1).sum())
+    e16 = int((((d16 ^ up) & m) != 0).any(1).sum())
+    ci = 1.96 * np.sqrt(2.0 * max(e32, 1)) + 2
+    print("%s at %.1f dB: %d block errors with float32 LLRs, %d with float16 LLRs of %d frames (95 %% half-width %.1f); %d frames decided differently"
+          % (prog, ebn0, e32, e16, B, ci, int((d32 != d16).any(1).sum())))
+    assert abs(e32 - e16) <= ci
+    # an odd count exercises the conversion kernel's tail
+    d1, _ = eng.decode_llr(h[:3, :], packed=True)
+    assert (d1 == d16[:3]).all()
     eng.close()

@@ -85,6 +85,89 @@ def run_rank(rank, world, port, first, target, max_frames, chunk0, out):
     dist.destroy_process_group()
 
 
+def run_rank_pipelined(rank, world, port, first, target, max_frames, chunk0, out):
+    """The control flow of the pipelined pg_simulate (csrc/api.cu): round i+1 is planned from the frames PLANNED so far and is
+    computed (and all-reduced) before round i is merged; rounds in flight past the stopping point are discarded.  With a frame
+    budget only, every rank walks its fixed schedule and ONE all-reduce combines the ranks at the end."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from polardecoding_b200 import load_library, PgCounters
+    lib = load_library()
+    lib.pg_partition.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.pg_merge_round.argtypes = [C.POINTER(PgCounters), C.c_int, C.c_uint64, C.c_int, C.POINTER(PgCounters), C.POINTER(C.c_int), C.POINTER(C.c_uint64)]
+    lib.pg_truncate_info.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.POINTER(PgCounters)]
+    acc = PgCounters()
+    allreduces = 0
+
+    def count(info):
+        c = PgCounters()
+        lib.pg_truncate_info(info.ctypes.data, len(info), 1 << 62, C.byref(c))
+        return [c.frames, c.err_blocks, c.err_bits, c.tie_frames, c.crc_fail, c.bp_sweeps, 0, 0]
+
+    if target == 0:                                   # frame budget only
+        CH = 4096
+        nxt, left, tot = first, max_frames, np.zeros(8, dtype=np.int64)
+        while left:
+            chunk = min(CH, (left + world - 1) // world)
+            s, c = C.c_uint64(), C.c_uint64()
+            lib.pg_partition(nxt, chunk, world, rank, left, C.byref(s), C.byref(c))
+            tot += np.array(count(frame_info(s.value, c.value)), dtype=np.int64)
+            rnd = min(left, world * chunk)
+            left -= rnd
+            nxt += rnd
+        t = torch.from_numpy(tot)
+        dist.all_reduce(t)
+        allreduces += 1
+        out[rank] = (int(t[0]), int(t[1]), int(t[2]), int(t[3]), allreduces)
+        dist.destroy_process_group()
+        return
+
+    state = {"next": first, "chunk": chunk0, "planned": 0}
+    queue = []
+
+    def enqueue():
+        budget = (max_frames - state["planned"]) if max_frames else (1 << 62)
+        s, c = C.c_uint64(), C.c_uint64()
+        lib.pg_partition(state["next"], state["chunk"], world, rank, budget, C.byref(s), C.byref(c))
+        info = frame_info(s.value, c.value)
+        t = torch.zeros(world * 8, dtype=torch.int64)
+        t[rank * 8: rank * 8 + 8] = torch.tensor(count(info))
+        dist.all_reduce(t)                            # the exchange stream's ncclAllReduce of this round
+        queue.append((info, t))
+        state["planned"] += min(budget, world * state["chunk"])
+        state["next"] += world * state["chunk"]
+        state["chunk"] = min(state["chunk"] * 2, 4096)
+
+    enqueue()
+    allreduces += 1
+    while True:
+        if len(queue) < 2 and (not max_frames or state["planned"] < max_frames):
+            enqueue()
+            allreduces += 1
+        info, t = queue.pop(0)
+        rnd = (PgCounters * world)()
+        for q in range(world):
+            rnd[q].frames, rnd[q].err_blocks, rnd[q].err_bits, rnd[q].tie_frames = [int(v) for v in t[q * 8: q * 8 + 4]]
+        cut, need = C.c_int(), C.c_uint64()
+        lib.pg_merge_round(rnd, world, target, 1, C.byref(acc), C.byref(cut), C.byref(need))
+        if cut.value >= 0:
+            part = PgCounters()
+            if cut.value == rank:
+                lib.pg_truncate_info(info.ctypes.data, len(info), need.value, C.byref(part))
+            p = torch.tensor([part.frames, part.err_blocks, part.err_bits, part.tie_frames], dtype=torch.int64)
+            dist.all_reduce(p)
+            allreduces += 1
+            acc.frames += int(p[0]); acc.err_blocks += int(p[1]); acc.err_bits += int(p[2]); acc.tie_frames += int(p[3])
+            break
+        if acc.err_blocks >= target or (max_frames and acc.frames >= max_frames):
+            break
+        if not queue:
+            enqueue()
+            allreduces += 1
+    out[rank] = (acc.frames, acc.err_blocks, acc.err_bits, acc.tie_frames, allreduces)
+    dist.destroy_process_group()
+
+
 @pytest.mark.parametrize("target,max_frames,chunk0", [(50, 0, 64), (7, 0, 512), (0, 3000, 128), (1000, 2500, 100)])
 def test_two_ranks_reproduce_sequential_stop(target, max_frames, chunk0):
     world = 2
@@ -94,3 +177,18 @@ def test_two_ranks_reproduce_sequential_stop(target, max_frames, chunk0):
     mp.spawn(run_rank, args=(world, port, 12345, target, max_frames, chunk0, out), nprocs=world, join=True)
     want = sequential(12345, target, max_frames)
     assert out[0] == out[1] == want, (dict(out), want)
+
+
+@pytest.mark.parametrize("target,max_frames,chunk0", [(50, 0, 64), (7, 0, 512), (0, 3000, 128), (0, 20001, 64), (1000, 2500, 100), (3, 100, 64)])
+def test_two_ranks_pipelined_loop_reproduces_sequential_stop(target, max_frames, chunk0):
+    """same answer as the sequential walk although a round runs ahead of the merge; a frame budget alone needs one all-reduce"""
+    world = 2
+    port = 31500 + (os.getpid() + target + max_frames + chunk0) % 2000
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(run_rank_pipelined, args=(world, port, 12345, target, max_frames, chunk0, out), nprocs=world, join=True)
+    want = sequential(12345, target, max_frames)
+    assert out[0][:4] == out[1][:4] == want, (dict(out), want)
+    assert out[0][4] == out[1][4]
+    if target == 0:
+        assert out[0][4] == 1

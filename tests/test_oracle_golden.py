@@ -64,6 +64,28 @@ def test_kat_captured_results():
         assert "L = 8 bSNR = %.2f error block = %d run = %d" % (snr, eb, run) in cap
 
 
+def scl128_capture_runs(kat):
+    """{L: [(bSNR, run)...]} from the author's capture myResult_128/SCL128out_errblock50.dat (SCL_128.c with SEED = 1024, 50 errors,
+    one run of the program per list size, `#define L` edited by hand: SCL_128.c:16)"""
+    import re
+    runs = {}
+    for m in re.finditer(r"L = (\d+)\s+bSNR = ([0-9.]+)\s+error block = 50\s+run = (\d+)", kat["captures"]["myResult_128/SCL128out_errblock50.dat"]):
+        runs.setdefault(int(m.group(1)), []).append((float(m.group(2)), int(m.group(3))))
+    return runs
+
+
+def test_kat_scl128_every_list_size():
+    """K2 for all five list sizes of the capture (L = 2, 4, 8, 16, 32), frame-exact `run` columns up to 3.0 dB"""
+    kat = json.load(open(os.path.join(GOLD, "kat.json")))
+    runs = scl128_capture_runs(kat)
+    assert sorted(runs) == [2, 4, 8, 16, 32] and all(len(v) == 6 for v in runs.values())
+    o = Oracle("SCL_128")
+    for L, pts in runs.items():
+        pts = pts[:5]
+        res = o.simulate_ref(1, [p[0] for p in pts], 50, 1024, L=L)
+        assert [r[0] for r in res] == [p[1] for p in pts], (L, res)
+
+
 def test_kat_cascl():
     kat = json.load(open(os.path.join(GOLD, "kat.json")))
     # K4: CASCL_128, the SEED = 8392 block of myResult_128/CASCL_128_L8.txt (first three points: seconds on one core)
