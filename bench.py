@@ -324,6 +324,17 @@ def run_gpu_arm(a):
         fps_e = world * Be * reps / (ms_e / a.steps * 1e-3)
         out["e2e"] = {"value": fps_e * k_info / 1e9, "unit": "Gbit/s", "h2d_bytes_per_step": Be * reps * n * esz, "d2h_bytes_per_step": Be * reps * ((n // 8) + 4),
                       "frames_per_s": fps_e, "frames_per_step": world * Be * reps, "calls_per_step": reps, "timed_s": ms_e / 1e3}
+        if e2e == "f16":   # optional input format PG_LLR_F16: the same frames rounded to binary16, half the host-to-device bytes
+            h16 = torch.empty(Be * n, dtype=torch.float16).pin_memory()
+            h16.copy_(llr[: Be * n])
+
+            def e2e16_step():
+                for _ in range(reps):
+                    eng.decode_llr_host_ptr(h16.data_ptr(), 2, Be, h_out.data_ptr(), h_flags.data_ptr())
+            ms_h = wall_steps(torch, dist, world, e2e16_step, a.steps, 1, count)
+            fps_h = world * Be * reps / (ms_h / a.steps * 1e-3)
+            out["e2e_f16"] = {"value": fps_h * k_info / 1e9, "unit": "Gbit/s", "h2d_bytes_per_step": Be * reps * n * 2, "d2h_bytes_per_step": Be * reps * ((n // 8) + 4),
+                              "frames_per_s": fps_h, "note": "optional PG_LLR_F16 input (quantised LLRs: FER-level parity, tests/test_gpu_parity.py::test_fp16_llr_input)"}
         eng.close()
         del llr, truth, info
         return out
@@ -359,7 +370,7 @@ def run_gpu_arm(a):
         return res
 
     sampler.start()
-    res["cascl"] = bench_one("CASCL_1024_L8", EBN0_CASCL, B_CASCL, OPS_CASCL, tkey="cascl")
+    res["cascl"] = bench_one("CASCL_1024_L8", EBN0_CASCL, B_CASCL, OPS_CASCL, tkey="cascl", e2e="f16")
     res["bp"] = bench_one("BP_1024", EBN0_BP, B_BP, OPS_BP_SWEEP * 100, tkey="bp")
     res["bp_stop"] = bench_one("BP_1024", EBN0_BP, B_BP * 4, 0, bp_early_stop=1)
     res["bp_gm"] = bench_one("BP_1024", EBN0_BP, B_BP * 4, 0, e2e=False, bp_early_stop=3)      # optional codeword ("G-matrix") stop rule
@@ -394,7 +405,7 @@ def run_gpu_arm(a):
                            "partition": "rank r decodes its own Philox frame range; one NCCL all-reduce of the final counters",
                            "host_numa": numa},
                 "frames_per_s": r["frames_per_s"], "fer": r["fer"], "tie_frames": r["tie_frames"], "frames_counted": r["frames_counted"],
-                "timed_s": r["timed_s"], "roofline": r["roofline"], "e2e": r["e2e"], "gpu_launches": launches, "clocks": clocks,
+                "timed_s": r["timed_s"], "roofline": r["roofline"], "e2e": r["e2e"], "e2e_f16": r.get("e2e_f16"), "gpu_launches": launches, "clocks": clocks,
                 "bp_1024": {"value": res["bp"]["gbps"], "unit": "Gbit/s", "frames_per_s": res["bp"]["frames_per_s"], "ms_per_step": res["bp"]["ms_per_step"],
                             "frames_per_step": res["bp"]["frames_per_step"], "sweeps": 100, "fer": res["bp"]["fer"], "timed_s": res["bp"]["timed_s"],
                             "roofline": dict(res["bp"]["roofline"], frac_on_executed_work=res["bp"]["roofline"]["frac"] * OPS_BP_SWEEP_EXEC / OPS_BP_SWEEP,

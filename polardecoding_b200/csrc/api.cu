@@ -113,7 +113,7 @@ struct pg_ctx {
     ncclComm_t comm = nullptr;
     unsigned long long *d_xchg = nullptr;  // nranks*CNT_N
     // pipelined Monte-Carlo loop (pg_simulate): a ring of round slots, the counter exchange on its own stream
-    static constexpr int kRing = 3;
+    static constexpr int kRing = 4;
     cudaStream_t st_comm = nullptr;
     unsigned long long *d_rc[kRing] = {};      // this rank's counters of the round in the slot (CNT_N)
     unsigned long long *d_xm[kRing] = {};      // [nranks][CNT_N] exchange matrix of the round
@@ -799,7 +799,11 @@ static int ensure_ring(pg_ctx *ctx, size_t frames, bool want_info)
 {
     const size_t R = (size_t)ctx->p.nranks;
     if (!ctx->st_comm) {
-        CU(cudaStreamCreateWithFlags(&ctx->st_comm, cudaStreamNonBlocking));
+        {   // the exchange stream outranks the decode streams: its tiny kernels take the first SM slot that frees up
+            int lo = 0, hi = 0;
+            CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CU(cudaStreamCreateWithPriority(&ctx->st_comm, cudaStreamNonBlocking, hi));
+        }
         for (int r = 0; r < pg_ctx::kRing; r++) {
             CU(cudaMalloc(&ctx->d_rc[r], CNT_N * 8));
             CU(cudaMalloc(&ctx->d_xm[r], R * CNT_N * 8));
@@ -930,14 +934,17 @@ extern "C" int pg_simulate(pg_ctx *ctx, double ebn0_db, uint64_t first_frame, ui
         cudaStreamSynchronize(ctx->st);
         cudaStreamSynchronize(ctx->st_comm);
     };
-    // the BPR statistic sums on the device over everything that was decoded: no round may run past the stopping point then
-    const unsigned depth = ctx->bpr_ns ? 1u : 2u;
+    // Rounds in flight.  The decode kernels are persistent, so the exchange of round i finds a free SM only while round i+1 drains:
+    // the host learns about round i at the end of round i+1, and round i+2 must already be queued for the GPU not to idle -- three
+    // in flight.  (The ranks may then also drift apart by a round or two instead of meeting at every all-reduce.)
+    // The BPR statistic sums on the device over everything that was decoded: no round may run past the stopping point then.
+    const unsigned depth = ctx->bpr_ns ? 1u : (unsigned)(pg_ctx::kRing - 1);
     int rc = enqueue_next();
     if (rc) return rc;
     std::vector<pg_counters> xc((size_t)R);
     while (true) {
-        // keep one more round in flight while the host waits for the oldest one
-        if (head - tail < depth && (!max_frames || planned < max_frames)) {
+        // keep `depth` rounds in flight while the host waits for the oldest one
+        while (head - tail < depth && (!max_frames || planned < max_frames)) {
             rc = enqueue_next();
             if (rc) { drain(); return rc; }
         }
@@ -1037,6 +1044,12 @@ extern "C" int pg_comm_init(pg_ctx *ctx, const void *id128)
     std::memcpy(&id, id128, 128);
     ncclResult_t r = g_nccl.CommInitRank(&ctx->comm, ctx->p.nranks, id, ctx->p.rank);
     if (r != ncclSuccess) { ctx->err = std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"); ctx->comm = nullptr; return PG_ERR_NCCL; }
+    // NCCL connects its channels lazily, inside the first collective (about a second with eight ranks): do that here, not in the
+    // first round of a Monte-Carlo loop whose pipeline would sit idle behind it
+    CU(cudaMemsetAsync(ctx->d_xchg, 0, CNT_N * 8, ctx->st));
+    r = g_nccl.AllReduce(ctx->d_xchg, ctx->d_xchg, CNT_N, ncclUint64, ncclSum, ctx->comm, ctx->st);
+    if (r != ncclSuccess) { ctx->err = std::string("ncclAllReduce (warm-up): ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"); return PG_ERR_NCCL; }
+    CU(cudaStreamSynchronize(ctx->st));
     return PG_OK;
 }
 

@@ -141,7 +141,7 @@ def run_rank_pipelined(rank, world, port, first, target, max_frames, chunk0, out
     enqueue()
     allreduces += 1
     while True:
-        if len(queue) < 2 and (not max_frames or state["planned"] < max_frames):
+        while len(queue) < 3 and (not max_frames or state["planned"] < max_frames):   # pg_ctx::kRing - 1 rounds in flight
             enqueue()
             allreduces += 1
         info, t = queue.pop(0)
