@@ -188,6 +188,20 @@ __device__ __forceinline__ void prefetch_l1(const void *p)
     (void)p;
 #endif
 }
+#ifndef POLAR_COMPACT
+#define POLAR_COMPACT 1  // fewer inline copies of the leaf body and of the four-CHK block in the hot loop (instruction cache)
+#endif
+#ifndef POLAR_FRZ4
+#define POLAR_FRZ4 1     // straight-line body for leaf groups of four frozen bits
+#endif
+// Measured on B200 (CA-SCL 1024 L=8; fp32 / fp64 M frames/s, tools/ab.py): round-1 loop 13.44 / 5.03; POLAR_COMPACT 13.46 / 6.06 (the
+// fp64 instantiation, whose CHK is twice as long, comes back under the instruction-cache cliff); POLAR_COMPACT + POLAR_VIRT 11.1 /
+// 5.65 although the HBM traffic drops by 14 % and long_scoreboard from 3.0 to 2.0 per issue: the two extra loops push the fp32
+// kernel from 3 050 to 3 900 SASS instructions, over the same cliff (3 740 without the frozen-group body: 12.2).  So POLAR_VIRT is
+// off in the product; the CPU emulator build turns it on to keep its logic pinned to the oracle.
+#ifndef POLAR_VIRT
+#define POLAR_VIRT 0     // 1: two g-outputs of the top LLR stages are recomputed instead of stored (see f_virtual)
+#endif
 #ifndef POLAR_PF_MAX
 #define POLAR_PF_MAX 0   // g-layers up to this stage get their source prefetched into the L1 one leaf group ahead (0: off)
 #endif
@@ -422,6 +436,71 @@ list_decode_kernel(const ListArgs a)
             if (tdst) tm_wait_st();
         };
 
+        // ---- two g-outputs of the top stages are VIRTUAL: never stored, recomputed where they are consumed ----------------
+        // A g-layer output is one add per node, but at the two top stages it is also the bulk of the scratch traffic: each value is
+        // written once and read twice, both times long after the L2 has dropped it (a top g-layer takes a warp ~200 us).  So, for
+        // T = LOGN-1 and S = LOGN-2 (stages 9 and 8 of N = 1024), with indices counting V4 groups:
+        //   stage T, second half (g from the channel, at leaf N/2):        vT[m]  = ch[m + N/8] + flip(ch[m], B[T] nibble m)
+        //   stage S, block 1 (g from the STORED first half of T, at N/4):  vS1[i] = sT[i + N/16] + flip(sT[i], B[S] nibble i)
+        // are not written.  Their consumers -- the f-layers below them (at N/2 and N/4), the g-layer that opens stage S-1 at 3N/8
+        // and the g-layer at S at 3N/4 -- read the channel / the stored half instead, which all paths of a frame share (one 16-byte
+        // request serves the frame's L lanes), plus the path's partial-sum bits.  The pointer field of T and the bit pointers of
+        // B[T], B[S] keep doing their job: B[S] of leaf N/4 lives until 3N/4, B[T] until the end.  (Stage S block 3, a g of a g,
+        // is stored: recomputing it means eight channel loads per value.)
+        // Off (virt == false) when the cooperative prefix runs its in-place butterfly in stage T's array.
+        auto nib = [&](const uint32_t *bw, int i) -> uint32_t { return (bw[(i >> 3) * 32] >> ((i & 7) * 4)) & 0xFu; };
+        const uint32_t *vbits = nullptr;   // B[T] (mode 0) or B[S] (mode 1) of this path
+        const V4 *vsrc = nullptr;          // the channel (mode 0) or the stored first half of stage T (mode 1)
+        int vstride = 1, vhalf = 0;
+        struct VRaw { V4 up, lo; uint32_t nb; };
+        auto v_begin = [&](int mode) {
+            constexpr int T = LOGN - 1, S = LOGN - 2;
+            if (mode == 0) { vbits = bits_at(T >= 6 ? T : 6) + fbase + bfield(T >= 6 ? T : 6); vsrc = ch4; vstride = 1; vhalf = N >> 3; }
+            else { vbits = bits_at(S >= 6 ? S : 6) + fbase + bfield(S >= 6 ? S : 6); vsrc = stage_at(T) + fbase + pfield(T); vstride = 32; vhalf = N >> 4; }
+        };
+        auto v_load = [&](int i) -> VRaw {
+            VRaw r;
+            r.up = ldv(vsrc + i * vstride);
+            r.lo = ldv(vsrc + (i + vhalf) * vstride);
+            r.nb = nib(vbits, i);
+            return r;
+        };
+        // f-layer producing stage s from the virtual stage s+1 (mode 0: s = S from vT; mode 1: s = S-1 from vS1); operands of the next
+        // step are in flight while the four CHKs of this one run
+        auto f_virtual = [&](int s, int mode) {
+            const int cnt4 = 1 << (s - 2);
+            v_begin(mode);
+            const bool tdst = in_tm(s);
+            V4 *dst = tdst ? nullptr : stage_at(s) + lane;
+            VRaw ra = v_load(0), rb = v_load(cnt4);
+#pragma unroll 1
+            for (int i4 = 0; i4 < cnt4; i4++) {
+                const V4 x = g4<real>(ra.up, ra.lo, ra.nb), y = g4<real>(rb.up, rb.lo, rb.nb);
+                if (i4 + 1 < cnt4) { ra = v_load(i4 + 1); rb = v_load(i4 + 1 + cnt4); }
+                const V4 o = f4<real>(x, y);
+                if (tdst) tm_st(tm, tmoff(s) + i4, o);
+                else stv(dst + i4 * 32, o);
+            }
+            if (tdst) tm_wait_st();
+        };
+        // g-layer producing stage t from the virtual stage t+1 (mode 0: t = S at 3N/4 from vT; mode 1: t = S-1 at 3N/8 from vS1)
+        auto g_virtual = [&](int t, int mode) {
+            const int cnt4 = 1 << (t - 2);
+            v_begin(mode);
+            const uint32_t *bsrc = bits_at(t) + fbase + bfield(t);   // t >= LOGN-3 >= 6
+            const bool tdst = in_tm(t);
+            V4 *dst = tdst ? nullptr : stage_at(t) + lane;
+#pragma unroll 1
+            for (int i4 = 0; i4 < cnt4; i4 += 2) {   // eight loads in flight per lane, as in g_layer
+                const VRaw u0 = v_load(i4), l0 = v_load(i4 + cnt4), u1 = v_load(i4 + 1), l1 = v_load(i4 + 1 + cnt4);
+                const V4 o0 = g4<real>(g4<real>(u0.up, u0.lo, u0.nb), g4<real>(l0.up, l0.lo, l0.nb), nib(bsrc, i4));
+                const V4 o1 = g4<real>(g4<real>(u1.up, u1.lo, u1.nb), g4<real>(l1.up, l1.lo, l1.nb), nib(bsrc, i4 + 1));
+                if (tdst) { tm_st(tm, tmoff(t) + i4, o0); tm_st(tm, tmoff(t) + i4 + 1, o1); }
+                else { stv(dst + i4 * 32, o0); stv(dst + (i4 + 1) * 32, o1); }
+            }
+            if (tdst) tm_wait_st();
+        };
+
         // ---- one leaf: frozen -> PM only; information -> decide (SC) or fork/prune (list) ------------------
         // first: the even leaf of a pair (its stage-1 values are read again by the odd leaf); keep2: stage 2 is still needed
         auto leaf = [&](bool info, real lam, bool first, bool keep2) -> uint32_t {
@@ -559,6 +638,10 @@ list_decode_kernel(const ListArgs a)
         // block that holds the first information bit is copied into slot 0's arrays of every stage, which is the state the
         // loop below resumes from (all pointer fields 0, all partial sums 0).
         int j4_start = 0;
+        // virtual top stages (see f_virtual): not when the prefix butterfly would work in stage T's array (first information bit
+        // beyond leaf N/4), and only where the three stages involved are scratch stages with their bits in a bit array
+        const bool virt = POLAR_VIRT && LOGN >= 9 && (LOGN - 3 >= GLO || HAS_TM) && LOGN - 3 >= 6 &&
+                          !(L > 1 && a.coop_groups >= 2 && 4 * a.coop_groups > (N >> 2));
         if (L > 1 && a.coop_groups >= 2) {
             int P = a.coop_groups;
             if (P > N / 8) P = N / 8;               // keep the subtree inside the first half: its root is then an f-layer output
@@ -646,6 +729,7 @@ list_decode_kernel(const ListArgs a)
             } else {
                 V4 a3, b3;
                 int top = 3;
+                bool stored3 = false;
                 if (j4 & 2) {  // g at stage 3 from stage 4 (via the pointer word)
                     const uint32_t bw = Blow >> 4;
                     V4 u, l;
@@ -659,9 +743,29 @@ list_decode_kernel(const ListArgs a)
                     if (j4 != 0) {
                         s = __ffs(j4) - 1 + 2;
                         top = s;
-                        g_layer(s);
-                        s--;
+                        if (virt && s == LOGN - 1) {          // leaf N/2: f-layer at S straight from the channel
+                            f_virtual(LOGN - 2, 0);
+                            s = LOGN - 3;
+                        } else if (virt && s == LOGN - 2 && j4 == (N >> 4)) {   // leaf N/4: f-layer at S-1 from the virtual block 1 of S
+                            f_virtual(LOGN - 3, 1);
+                            s = LOGN - 4;
+                        } else if (virt && s == LOGN - 2) {   // leaf 3N/4: g-layer at S from the virtual half of T (stored)
+                            g_virtual(s, 0);
+                            s--;
+                        } else if (virt && s == LOGN - 3 && j4 == 3 * (N >> 5)) {  // leaf 3N/8: g-layer at S-1 from the virtual block 1 of S
+                            g_virtual(s, 1);
+                            s--;
+                        } else {
+                            g_layer(s);
+                            s--;
+                        }
                     }
+#if POLAR_COMPACT
+#pragma unroll 1
+                    for (; s >= 3; s--) f_layer(s, false);   // stage 3 too: one copy of the four-CHK block less (code size: see f4)
+                    ld_own2(3, 0, 1, a3, b3);
+                    stored3 = true;
+#else
 #pragma unroll 1
                     for (; s >= 4; s--) f_layer(s, false);
                     V4 u, l;                 // own home
@@ -669,8 +773,10 @@ list_decode_kernel(const ListArgs a)
                     a3 = f4<real>(u, l);
                     ld_own2(4, 1, 3, u, l);
                     b3 = f4<real>(u, l);
+#endif
                 }
-                if (in_tm(3)) {
+                if (stored3) {
+                } else if (in_tm(3)) {
                     tm_st(tm, tmoff(3), a3);
                     tm_st(tm, tmoff(3) + 1, b3);
                     tm_wait_st();
@@ -696,7 +802,7 @@ list_decode_kernel(const ListArgs a)
             }
             ug = 0;
             const uint32_t inib = a.m.info[j4 >> 3] >> ((j4 & 7) * 4);  // which of the four leaves carry information
-            if (L > 1 && (inib & 0xFu) == 0u) {
+            if (POLAR_FRZ4 && L > 1 && (inib & 0xFu) == 0u) {
                 // four frozen leaves (every decision 0): the two in-register levels are a fixed butterfly, so the four leaf LLRs and
                 // their table look-ups are independent; only the four path-metric additions keep the leaf order (SCL_1024.c:489-500)
                 const real f0 = chk_lean<real>(s2[0], s2[2]), f1 = chk_lean<real>(s2[1], s2[3]);
@@ -723,10 +829,23 @@ list_decode_kernel(const ListArgs a)
                     s1[0] = s2[2] + RT::flip(s2[0], (ug ^ (ug >> 1)) & 1u);
                     s1[1] = s2[3] + RT::flip(s2[1], (ug >> 1) & 1u);
                 }
+#if POLAR_COMPACT
+                // the two leaves of the pair go through ONE copy of the leaf body (code size: see f4)
+                uint32_t ua = 0;
+#pragma unroll 1
+                for (int q = 0; q < 2; q++) {
+                    real lam;
+                    if (q == 0) lam = chk_lean<real>(s1[0], s1[1]);   // f at stage 0
+                    else lam = s1[1] + RT::flip(s1[0], ua);           // g at stage 0
+                    ua = leaf((inib >> (2 * p + q)) & 1u, lam, q == 0, p == 0);
+                    ug |= ua << (2 * p + q);  // ug travels with the path when the next leaf clones it
+                }
+#else
                 const uint32_t ua = leaf((inib >> (2 * p)) & 1u, chk_lean<real>(s1[0], s1[1]), true, p == 0);   // f at stage 0
                 ug |= ua << (2 * p);  // ug travels with the path when the next leaf clones it
                 const uint32_t ub = leaf((inib >> (2 * p + 1)) & 1u, s1[1] + RT::flip(s1[0], ua), false, p == 0);  // g at stage 0
                 ug |= ub << (2 * p + 1);
+#endif
             }
 
             // ---- partial sums of the finished 4-block, pushed up while the block closes larger blocks -------
