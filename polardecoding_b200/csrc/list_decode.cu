@@ -188,8 +188,18 @@ __device__ __forceinline__ void prefetch_l1(const void *p)
     (void)p;
 #endif
 }
-#ifndef POLAR_COMPACT
-#define POLAR_COMPACT 1  // fewer inline copies of the leaf body and of the four-CHK block in the hot loop (instruction cache)
+// Measured (CA-SCL 1024 L=8, fp32 / fp64 M frames/s): fused g+f layers 12.72 / 5.31 against 13.54 / 6.08 without -- the fused loop
+// keeps sixteen operand registers in flight on top of the four CHKs, so the compiler re-derives its addresses every step: +6 % executed
+// instructions for -12 % HBM reads and long_scoreboard 3.1 -> 2.25 per issue; the issue slots are worth more than the stalls.
+#ifndef POLAR_FUSE_GF
+#define POLAR_FUSE_GF 0  // g-layers at stages >= 5 run fused with the f-layer below them (see gf_layer): 0 never, 1 always, 2 fp64 only
+#endif
+// fewer inline copies of the leaf body / of the four-CHK block in the hot loop (instruction cache): 0 never, 1 always, 2 fp64 only
+#ifndef POLAR_FOLD_LEAF
+#define POLAR_FOLD_LEAF 2
+#endif
+#ifndef POLAR_FOLD_F3
+#define POLAR_FOLD_F3 1
 #endif
 #ifndef POLAR_FRZ4
 #define POLAR_FRZ4 1     // straight-line body for leaf groups of four frozen bits
@@ -274,6 +284,9 @@ list_decode_kernel(const ListArgs a)
     using V4 = vec4<real>;
     constexpr int N = C::N, W = C::W, FPW = C::FPW, TOP = C::TOP, BTOP = C::BTOP, BLO = C::BLO, GLO = C::GLO;
     constexpr bool HAS_TM = C::HAS_TM;
+    constexpr bool FOLD_LEAF = POLAR_FOLD_LEAF == 1 || (POLAR_FOLD_LEAF == 2 && sizeof(real) == 8);
+    constexpr bool FOLD_F3 = POLAR_FOLD_F3 == 1 || (POLAR_FOLD_F3 == 2 && sizeof(real) == 8);
+    constexpr bool FUSE_GF = POLAR_FUSE_GF == 1 || (POLAR_FUSE_GF == 2 && sizeof(real) == 8);
     constexpr int PWID = PW::W;
     constexpr ptr_t PMASK = (ptr_t)((1u << PWID) - 1);
     constexpr uint32_t LMASK = (L == 32) ? 0xffffffffu : ((1u << (L & 31)) - 1u);  // lanes of one frame
@@ -434,6 +447,35 @@ list_decode_kernel(const ListArgs a)
                 bw >>= 16;
             }
             if (tdst) tm_wait_st();
+        };
+
+        // ---- g-layer at stage t (t >= 5) FUSED with the f-layer below it ---------------------------------------------------
+        // The f-layer at t-1 pairs node i with node i + h (h = half of stage t), so one step loads the four source groups of those
+        // two g-outputs, stores them (the g-layer that opens stage t-1 half a block later reads them again) and feeds them to the
+        // four CHKs from registers: the f-layer does not re-read stage t, and the memory latency of the g-layer -- one add per node,
+        // 23 % of the warp samples at 8 % of the instructions as a loop of its own -- hides behind the CHKs of the previous step.
+        auto gf_layer = [&](int t) {
+            const int h = 1 << (t - 3);              // V4 groups per half of stage t = outputs of the f-layer
+            V4 *dg = stage_at(t) + lane, *df = stage_at(t - 1) + lane;
+            const V4 *src = ch4;
+            int stride = 1;
+            if (t + 1 != LOGN) { src = stage_at(t + 1) + fbase + pfield(t + 1); stride = 32; }
+            const int oh = h * stride;               // element offsets of the three other source groups of a step
+            const uint32_t *bsrc = (t >= 6) ? bits_at(t) + fbase + bfield(t) : nullptr;
+            uint32_t w0 = B5, w1 = B5 >> 16;         // t == 5: B[5] is a register (nibbles 0..3 and 4..7)
+            V4 a0 = ldv(src), a1 = ldv(src + 2 * oh), b0 = ldv(src + oh), b1 = ldv(src + 3 * oh);
+#pragma unroll 1
+            for (int i = 0; i < h; i++, dg += 32, df += 32) {
+                if (t >= 6 && (i & 7) == 0) { w0 = bsrc[(i >> 3) * 32]; w1 = bsrc[((i + h) >> 3) * 32]; }
+                const V4 gi = g4<real>(a0, a1, w0 & 0xFu), gh = g4<real>(b0, b1, w1 & 0xFu);
+                w0 >>= 4; w1 >>= 4;
+                // operands of the next step (the last step re-reads its own: an unconditional load keeps the loop body straight)
+                if (i + 1 < h) src += stride;
+                a0 = ldv(src); a1 = ldv(src + 2 * oh); b0 = ldv(src + oh); b1 = ldv(src + 3 * oh);
+                stv(dg, gi);
+                stv(dg + h * 32, gh);
+                stv(df, f4<real>(gi, gh));
+            }
         };
 
         // ---- two g-outputs of the top stages are VIRTUAL: never stored, recomputed where they are consumed ----------------
@@ -755,25 +797,28 @@ list_decode_kernel(const ListArgs a)
                         } else if (virt && s == LOGN - 3 && j4 == 3 * (N >> 5)) {  // leaf 3N/8: g-layer at S-1 from the virtual block 1 of S
                             g_virtual(s, 1);
                             s--;
+                        } else if (FUSE_GF && !HAS_TM && s >= 5) {   // g-layer fused with the f-layer below it
+                            gf_layer(s);
+                            s -= 2;
                         } else {
                             g_layer(s);
                             s--;
                         }
                     }
-#if POLAR_COMPACT
+                    if (FOLD_F3) {
 #pragma unroll 1
-                    for (; s >= 3; s--) f_layer(s, false);   // stage 3 too: one copy of the four-CHK block less (code size: see f4)
-                    ld_own2(3, 0, 1, a3, b3);
-                    stored3 = true;
-#else
+                        for (; s >= 3; s--) f_layer(s, false);   // stage 3 too: one copy of the four-CHK block less (code size: see f4)
+                        ld_own2(3, 0, 1, a3, b3);
+                        stored3 = true;
+                    } else {
 #pragma unroll 1
-                    for (; s >= 4; s--) f_layer(s, false);
-                    V4 u, l;                 // own home
-                    ld_own2(4, 0, 2, u, l);
-                    a3 = f4<real>(u, l);
-                    ld_own2(4, 1, 3, u, l);
-                    b3 = f4<real>(u, l);
-#endif
+                        for (; s >= 4; s--) f_layer(s, false);
+                        V4 u, l;                 // own home
+                        ld_own2(4, 0, 2, u, l);
+                        a3 = f4<real>(u, l);
+                        ld_own2(4, 1, 3, u, l);
+                        b3 = f4<real>(u, l);
+                    }
                 }
                 if (stored3) {
                 } else if (in_tm(3)) {
@@ -829,23 +874,23 @@ list_decode_kernel(const ListArgs a)
                     s1[0] = s2[2] + RT::flip(s2[0], (ug ^ (ug >> 1)) & 1u);
                     s1[1] = s2[3] + RT::flip(s2[1], (ug >> 1) & 1u);
                 }
-#if POLAR_COMPACT
-                // the two leaves of the pair go through ONE copy of the leaf body (code size: see f4)
-                uint32_t ua = 0;
+                if (FOLD_LEAF) {
+                    // the two leaves of the pair go through ONE copy of the leaf body (code size: see f4)
+                    uint32_t ua = 0;
 #pragma unroll 1
-                for (int q = 0; q < 2; q++) {
-                    real lam;
-                    if (q == 0) lam = chk_lean<real>(s1[0], s1[1]);   // f at stage 0
-                    else lam = s1[1] + RT::flip(s1[0], ua);           // g at stage 0
-                    ua = leaf((inib >> (2 * p + q)) & 1u, lam, q == 0, p == 0);
-                    ug |= ua << (2 * p + q);  // ug travels with the path when the next leaf clones it
+                    for (int q = 0; q < 2; q++) {
+                        real lam;
+                        if (q == 0) lam = chk_lean<real>(s1[0], s1[1]);   // f at stage 0
+                        else lam = s1[1] + RT::flip(s1[0], ua);           // g at stage 0
+                        ua = leaf((inib >> (2 * p + q)) & 1u, lam, q == 0, p == 0);
+                        ug |= ua << (2 * p + q);  // ug travels with the path when the next leaf clones it
+                    }
+                } else {
+                    const uint32_t ua = leaf((inib >> (2 * p)) & 1u, chk_lean<real>(s1[0], s1[1]), true, p == 0);   // f at stage 0
+                    ug |= ua << (2 * p);  // ug travels with the path when the next leaf clones it
+                    const uint32_t ub = leaf((inib >> (2 * p + 1)) & 1u, s1[1] + RT::flip(s1[0], ua), false, p == 0);  // g at stage 0
+                    ug |= ub << (2 * p + 1);
                 }
-#else
-                const uint32_t ua = leaf((inib >> (2 * p)) & 1u, chk_lean<real>(s1[0], s1[1]), true, p == 0);   // f at stage 0
-                ug |= ua << (2 * p);  // ug travels with the path when the next leaf clones it
-                const uint32_t ub = leaf((inib >> (2 * p + 1)) & 1u, s1[1] + RT::flip(s1[0], ua), false, p == 0);  // g at stage 0
-                ug |= ub << (2 * p + 1);
-#endif
             }
 
             // ---- partial sums of the finished 4-block, pushed up while the block closes larger blocks -------
