@@ -370,14 +370,29 @@ def run_gpu_arm(a):
         return res
 
     sampler.start()
-    res["cascl"] = bench_one("CASCL_1024_L8", EBN0_CASCL, B_CASCL, OPS_CASCL, tkey="cascl", e2e="f16")
-    res["bp"] = bench_one("BP_1024", EBN0_BP, B_BP, OPS_BP_SWEEP * 100, tkey="bp")
-    res["bp_stop"] = bench_one("BP_1024", EBN0_BP, B_BP * 4, 0, bp_early_stop=1)
-    res["bp_gm"] = bench_one("BP_1024", EBN0_BP, B_BP * 4, 0, e2e=False, bp_early_stop=3)      # optional codeword ("G-matrix") stop rule
-    res["bp_h2"] = bench_one("BP_1024", EBN0_BP, B_BP, OPS_BP_SWEEP * 100, real="h2", e2e=False)   # optional packed-half mode (FER-only parity)
+    legs = set(a.legs.split(",")) if a.legs else None           # development aid (profiling one kernel): the driver runs all legs
+
+    def want(name):
+        return legs is None or name in legs
+    res["cascl"] = bench_one("CASCL_1024_L8", EBN0_CASCL, B_CASCL, OPS_CASCL, tkey="cascl", e2e="f16" if legs is None else False)
+    if want("bp"):
+        res["bp"] = bench_one("BP_1024", EBN0_BP, B_BP, OPS_BP_SWEEP * 100, tkey="bp", e2e=legs is None)
+    if legs is None:
+        res["bp_stop"] = bench_one("BP_1024", EBN0_BP, B_BP * 4, 0, bp_early_stop=1)
+        res["bp_gm"] = bench_one("BP_1024", EBN0_BP, B_BP * 4, 0, e2e=False, bp_early_stop=3)      # optional codeword ("G-matrix") stop rule
+        res["bp_h2"] = bench_one("BP_1024", EBN0_BP, B_BP, OPS_BP_SWEEP * 100, real="h2", e2e=False)   # optional packed-half mode (FER-only parity)
     # the bit-exact (fp64) instantiation of both kernels: the configuration that meets north_star's "bit-exact decisions" to the letter
-    res["cascl64"] = bench_one("CASCL_1024_L8", EBN0_CASCL, B_CASCL // 3, OPS_CASCL, tkey="cascl64", real="f64")
-    res["bp64"] = bench_one("BP_1024", EBN0_BP, B_BP // 2, OPS_BP_SWEEP * 100, tkey="bp64", real="f64")
+    if want("cascl64"):
+        res["cascl64"] = bench_one("CASCL_1024_L8", EBN0_CASCL, B_CASCL // 3, OPS_CASCL, tkey="cascl64", real="f64", e2e=legs is None)
+    if want("bp64"):
+        res["bp64"] = bench_one("BP_1024", EBN0_BP, B_BP // 2, OPS_BP_SWEEP * 100, tkey="bp64", real="f64", e2e=legs is None)
+    if legs is not None:
+        sampler.stop()
+        if rank == 0:
+            print(json.dumps({k: {"frames_per_s": v["frames_per_s"], "frames_per_step": v["frames_per_step"], "roofline": v["roofline"]} for k, v in res.items()}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     res["bp64_stop"] = bench_one("BP_1024", EBN0_BP, B_BP * 2, 0, real="f64", bp_early_stop=1)
     # the other configs[] of BASELINE.json (device-resident inputs; the N = 128 programs have K = 64)
     res["sc_128"] = bench_one("SC_128", 2.0, 1 << 22, OPS_SC_128, e2e=False, n=128, k_info=64)
@@ -452,6 +467,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--legs", default=None, help="development aid: only these device-resident legs (cascl always; bp, cascl64, bp64), short JSON")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference_arm(a)

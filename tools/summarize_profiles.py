@@ -25,14 +25,18 @@ def raw(rep):
 
 
 try:  # frames per launch of the profiled command = frames per step of the bench line of the same round
-    _b = json.load(open(os.path.join(ROOT, "gpurun_out", "bench_r1b.json")))
-    FRAMES = {"cascl": _b["config"]["frames_per_step"], "bp": _b["bp_1024"]["frames_per_step"], "bph2": _b["bp_1024"]["frames_per_step"]}
+    _b = json.load(open(os.path.join(ROOT, "gpurun_out", "bench_%s.json" % tag)))
+    FRAMES = {"cascl": _b["config"]["frames_per_step"], "bp": _b["bp_1024"]["frames_per_step"], "bph2": _b["bp_1024"]["frames_per_step"],
+              "bp64": _b.get("f64_parity_mode", {}).get("bp_1024", {}).get("frames_per_step")}
 except Exception:
     FRAMES = {}
 traffic = {"_note": "dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the kernel inside `python bench.py --steps 2 --warmup 3 --no-cpu`, "
                     "ncu --set full --clock-control none (profiles/%s_*_summary.txt)" % tag}
-for key, title in (("cascl", "CA-SCL N=1024 L=8 fp32 list kernel"), ("bp", "BP N=1024 fp32, 100 sweeps"), ("bph2", "BP N=1024 packed-half mode (optional flag)")):
-    rep = os.path.join(ROOT, "gpurun_out", "prof_%s_r1_final2.ncu-rep" % key)
+for key, title in (("cascl", "CA-SCL N=1024 L=8 fp32 list kernel"), ("cascl64", "CA-SCL N=1024 L=8 fp64 (bit-exact) list kernel, one quarter-grid launch"),
+                   ("bp", "BP N=1024 fp32, 100 sweeps"), ("bp64", "BP N=1024 fp64 (bit-exact), 100 sweeps"), ("bph2", "BP N=1024 packed-half mode (optional flag)")):
+    rep = os.path.join(ROOT, "gpurun_out", "prof_%s_%s.ncu-rep" % (key, tag))
+    if not os.path.exists(rep):
+        rep = os.path.join(ROOT, "gpurun_out", "prof_%s_r1_final2.ncu-rep" % key)
     if not os.path.exists(rep):
         continue
     v, units = raw(rep)
@@ -49,11 +53,11 @@ for key, title in (("cascl", "CA-SCL N=1024 L=8 fp32 list kernel"), ("bp", "BP N
     tot = gb(v["dram__bytes_read.sum"], units["dram__bytes_read.sum"]) + gb(v["dram__bytes_write.sum"], units["dram__bytes_write.sum"])
     traffic[key] = {"kernel": v.get("Kernel Name", ""), "dram_bytes_per_launch": tot, "grid": int(v["launch__grid_size"]),
                     "time_ms_under_ncu": float(v["gpu__time_duration.sum"]) * {"ms": 1.0, "us": 1e-3, "s": 1e3}.get(units["gpu__time_duration.sum"], 1.0),
-                    "frames_per_launch": FRAMES.get(key)}
+                    "frames_per_launch": FRAMES.get(key) if key != "cascl64" else int(v["launch__grid_size"]) * 4}
 json.dump(traffic, open(os.path.join(ROOT, "profiles", "%s_traffic.json" % tag), "w"), indent=1)
 
 # launch list
-lc = os.path.join(ROOT, "gpurun_out", "launches_r1b.csv")
+lc = os.path.join(ROOT, "gpurun_out", "launches_%s.csv" % tag)
 if os.path.exists(lc):
     rows = [r for r in csv.reader(l for l in open(lc) if not l.startswith("==")) if r]
     h = rows[0]
