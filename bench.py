@@ -397,9 +397,11 @@ def run_gpu_arm(a):
     # the other configs[] of BASELINE.json (device-resident inputs; the N = 128 programs have K = 64)
     res["sc_128"] = bench_one("SC_128", 2.0, 1 << 22, OPS_SC_128, e2e=False, n=128, k_info=64)
     res["bp_128"] = bench_one("BP_128", 2.5, 1 << 19, OPS_BP_128_SWEEP * 100, e2e=False, n=128, k_info=64)
-    res["sc_1024"] = bench_one("SC_1024", 2.0, 3 << 19, OPS_SC_1024, e2e=False)
+    res["sc_1024"] = bench_one("SC_1024", 2.0, 3 << 17, OPS_SC_1024, e2e=False)   # 1.5 GB of LLRs (> L2); one frame per lane reads 32 rows per request
     res["scl_1024"] = bench_one("SCL_1024", 2.0, 3 << 18, OPS_SCL_1024, e2e=False)
-    sim = bench_simulate("CASCL_1024_L8", EBN0_CASCL, 1.0)
+    # the author's deepest list size (myResult_1024/CASCL_L32.dat): one frame per warp; ops ~ 4 x the L = 8 count except the 64-candidate selection
+    res["cascl_l32"] = bench_one("CASCL_1024_L8", EBN0_CASCL, 3 << 17, 4 * (OPS_CASCL - 533 * 160) + 533 * 6 * 160, e2e=False, list_size=32)
+    sim = bench_simulate("CASCL_1024_L8", EBN0_CASCL, 2.0)
     clocks = sampler.stop()
 
     cpu = None
@@ -449,7 +451,8 @@ def run_gpu_arm(a):
                                                   fixed_point_stop=leg(res["bp64_stop"], sweeps_per_frame=res["bp64_stop"]["sweeps_per_frame"],
                                                                        note="bit-exact AND early-stopped: the sweeps after the fixed point change nothing (BP_1024.c:393 runs them anyway)"))}
         line["configs"] = {"note": "the other configs[] of BASELINE.json, device-resident inputs, fp32; ops_per_frame from SURVEY 8d",
-                           "sc_128": leg(res["sc_128"]), "bp_128": leg(res["bp_128"], sweeps=100), "sc_1024": leg(res["sc_1024"]), "scl_1024": leg(res["scl_1024"])}
+                           "sc_128": leg(res["sc_128"]), "bp_128": leg(res["bp_128"], sweeps=100), "sc_1024": leg(res["sc_1024"]), "scl_1024": leg(res["scl_1024"]),
+                           "cascl_1024_l32": leg(res["cascl_l32"], note="L = 32 (SURVEY 8f.2): ops_per_frame is an estimate, 4 x the L = 8 count with a 64-candidate selection")}
         line["simulate"] = dict(sim, note="pg_simulate = channel + decode + count + counter exchange, wall clock, max over ranks",
                                 collective=("ncclAllReduce (sum) of %d x 8 u64 per round on a second stream; ONE at the end of a frame-budget run" % world) if world > 1 else "none (1 rank)",
                                 frac_of_kernel_rate={k: v["frames_per_s"] / r["frames_per_s"] for k, v in sim.items()})

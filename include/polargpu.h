@@ -206,6 +206,7 @@ uint64_t pg_kernel_launches(const pg_ctx *ctx);        /* kernels launched by th
 /* device time (ms, CUDA events on the ctx stream) of the last decode kernel and of the last channel kernel */
 int pg_last_kernel_ms(pg_ctx *ctx, float *decode_ms, float *channel_ms);
 const char *pg_version(void);
+int pg_device_count(void);                             /* usable (sm_100) devices 0..n-1; 0 without a driver or device */
 
 #ifdef __cplusplus
 }

@@ -133,7 +133,20 @@ struct pg_ctx {
         }                                                                                        \
     } while (0)
 
-extern "C" const char *pg_version(void) { return "polargpu 0.1 (sm_100a)"; }
+extern "C" const char *pg_version(void) { return "polargpu 0.2 (sm_100a)"; }
+
+extern "C" int pg_device_count(void)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess) return 0;
+    int ok = 0;
+    for (int d = 0; d < ndev; d++) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, d) == cudaSuccess && prop.major == 10) ok++;
+        else break;  // usable devices must be the ordinals 0..ok-1 (rank r runs on device r)
+    }
+    return ok;
+}
 
 extern "C" int pg_params_preset(pg_params *p, const char *prog)
 {

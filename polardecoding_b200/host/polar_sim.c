@@ -378,6 +378,18 @@ int main(int argc, char **argv)
     else if (pd->seed_mod) printf("SEED = %ld\n", (long)SEED);
     consume_stdin(p.N);
 
+    if (gpus > 1 && pd->fmt == F_BPR) { fprintf(stderr, "polar_sim: BPr_128 supports one GPU\n"); return 2; }
+    if (gpus > 1) { /* a rank whose device is missing would leave the others waiting in the NCCL rendezvous: check before forking.
+                       The probe runs in a child so that the parent forks its ranks without a CUDA context of its own. */
+        fflush(stdout);
+        pid_t pr = fork();
+        if (pr == 0) _exit(pg_device_count() >= (int)gpus ? 0 : 1);
+        int st = 0;
+        if (pr < 0 || waitpid(pr, &st, 0) < 0 || !WIFEXITED(st) || WEXITSTATUS(st) != 0) {
+            fprintf(stderr, "polar_sim: --gpus %ld needs that many sm_100 devices\n", gpus);
+            return 3;
+        }
+    }
     fflush(stdout);
     int rank = 0, have_id = 0;
     unsigned char id[128];
@@ -416,7 +428,6 @@ int main(int argc, char **argv)
             if (bpr && pg_bpr_reset(ctx)) die("pg_bpr_reset", ctx);
             if (pg_simulate(ctx, bSNR_dB, next_frame, (uint64_t)ble, (uint64_t)maxf, bpr ? 0 : 1, &c)) die("pg_simulate", ctx);
             if (bpr) {
-                if (gpus > 1) { fprintf(stderr, "polar_sim: BPr_128 supports one GPU\n"); return 2; }
                 if (pg_bpr_read(ctx, g_bprE)) die("pg_bpr_read", ctx);
             }
         }
