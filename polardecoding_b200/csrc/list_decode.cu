@@ -191,6 +191,9 @@ __device__ __forceinline__ void prefetch_l1(const void *p)
 // Measured (CA-SCL 1024 L=8, fp32 / fp64 M frames/s): fused g+f layers 12.72 / 5.31 against 13.54 / 6.08 without -- the fused loop
 // keeps sixteen operand registers in flight on top of the four CHKs, so the compiler re-derives its addresses every step: +6 % executed
 // instructions for -12 % HBM reads and long_scoreboard 3.1 -> 2.25 per issue; the issue slots are worth more than the stalls.
+#ifndef POLAR_F32_CTAS
+#define POLAR_F32_CTAS 32   // resident one-warp CTAs per SM the fp32 kernel is compiled for (64 registers per thread)
+#endif
 #ifndef POLAR_FUSE_GF
 #define POLAR_FUSE_GF 0  // g-layers at stages >= 5 run fused with the f-layer below them (see gf_layer): 0 never, 1 always, 2 fp64 only
 #endif
@@ -274,7 +277,7 @@ __device__ __forceinline__ vec4<real> g4(const vec4<real> &up, const vec4<real> 
 
 template <typename real, int LOGN, int L, int SMEM_TOP, int BITS_TOP, int TML, int TMH>
 __global__ void __launch_bounds__(ListCfg<real, LOGN, L, SMEM_TOP, BITS_TOP, TML, TMH>::THREADS,
-                                  (TMH > TML) ? ((TML > 3) ? 7 : 8) : ((sizeof(real) == 4) ? 32 : 24))
+                                  (TMH > TML) ? ((TML > 3) ? 7 : 8) : ((sizeof(real) == 4) ? POLAR_F32_CTAS : 24))
 list_decode_kernel(const ListArgs a)
 {
     using C = ListCfg<real, LOGN, L, SMEM_TOP, BITS_TOP, TML, TMH>;
