@@ -72,6 +72,9 @@ typedef struct pg_params {
     int device;            /* CUDA device ordinal */
     uint64_t seed;         /* Philox key */
     int rank, nranks;      /* frame-space partition for pg_simulate (see there) */
+    float llr_clip;        /* > 0: every channel LLR is clipped to [-llr_clip, +llr_clip] before decoding (optional receiver model,
+                              SURVEY 8f.3: what a fixed-point front end does; not in the reference, so 0 = off in every preset).
+                              Decisions equal the reference decoder's on the clipped LLRs (tests/test_gpu_parity.py) */
 } pg_params;
 
 #define PG_CRC24_POLY 0x1B2B117ull /* D^24+D^23+D^21+D^20+D^17+D^15+D^13+D^12+D^8+D^4+D^2+D+1 */

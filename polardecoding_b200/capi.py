@@ -21,7 +21,7 @@ class PgParams(C.Structure):
     _fields_ = [("N", C.c_int), ("K", C.c_int), ("crc_bits", C.c_int), ("crc_poly", C.c_uint64),
                 ("crc_systematic", C.c_int), ("decoder", C.c_int), ("list_size", C.c_int), ("iter_max", C.c_int),
                 ("bp_early_stop", C.c_int), ("real", C.c_int), ("data_mode", C.c_int), ("count_from", C.c_int),
-                ("device", C.c_int), ("seed", C.c_uint64), ("rank", C.c_int), ("nranks", C.c_int)]
+                ("device", C.c_int), ("seed", C.c_uint64), ("rank", C.c_int), ("nranks", C.c_int), ("llr_clip", C.c_float)]
 
 
 class PgCounters(C.Structure):

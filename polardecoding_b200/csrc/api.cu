@@ -234,7 +234,7 @@ static int ensure_pipe(pg_ctx *ctx, size_t frames, bool want_bytes)
         cudaFree(ctx->p_llr[s]); cudaFree(ctx->p_in[s]); cudaFree(ctx->p_uhat[s]); cudaFree(ctx->p_info[s]); cudaFree(ctx->p_bytes[s]);
         ctx->p_llr[s] = ctx->p_in[s] = nullptr; ctx->p_uhat[s] = ctx->p_info[s] = nullptr; ctx->p_bytes[s] = nullptr;
         CU(cudaMalloc(&ctx->p_llr[s], frames * N * (ctx->f64 ? 8 : 4)));
-        CU(cudaMalloc(&ctx->p_in[s], frames * N * (ctx->f64 ? 4 : 8)));
+        CU(cudaMalloc(&ctx->p_in[s], frames * N * 8));
         CU(cudaMalloc(&ctx->p_uhat[s], frames * W * 4));
         CU(cudaMalloc(&ctx->p_info[s], frames * 4));
         if (want_bytes) CU(cudaMalloc(&ctx->p_bytes[s], frames * N));
@@ -249,7 +249,7 @@ static int ensure_capacity(pg_ctx *ctx, size_t frames)
     free_buffers(ctx);
     const size_t N = ctx->p.N, W = ctx->W;
     CU(cudaMalloc(&ctx->d_llr, frames * N * (ctx->f64 ? 8 : 4)));
-    CU(cudaMalloc(&ctx->d_in, frames * N * (ctx->f64 ? 4 : 8)));
+    CU(cudaMalloc(&ctx->d_in, frames * N * 8));
     CU(cudaMalloc(&ctx->d_truth, frames * W * 4));
     CU(cudaMalloc(&ctx->d_uhat, frames * W * 4));
     CU(cudaMalloc(&ctx->d_info, frames * 4));
@@ -271,6 +271,7 @@ extern "C" int pg_create(const pg_params *p, pg_ctx **out)
     if (p->real != PG_REAL_F64 && p->real != PG_REAL_F32 && p->real != PG_REAL_H2) return fail(PG_ERR_ARG, "bad real");
     if (p->real == PG_REAL_H2 && p->decoder != PG_DEC_BP) return fail(PG_ERR_UNSUPPORTED, "PG_REAL_H2 is a BP-only mode");
     if (p->nranks < 1 || p->rank < 0 || p->rank >= p->nranks) return fail(PG_ERR_ARG, "bad rank/nranks");
+    if (!(p->llr_clip >= 0.0f)) return fail(PG_ERR_ARG, "llr_clip must be >= 0");
     const int L = (p->decoder == PG_DEC_SC) ? 1 : p->list_size;
     if (p->decoder != PG_DEC_BP && (L < 1 || L > 32 || (L & (L - 1)))) return fail(PG_ERR_ARG, "list_size must be 1,2,4,8,16,32");
     if ((p->decoder == PG_DEC_SCL || p->decoder == PG_DEC_CASCL) && L < 2) return fail(PG_ERR_ARG, "list decoders need list_size >= 2");
@@ -456,7 +457,12 @@ static int run_channel_to(pg_ctx *ctx, double ebn0_db, uint64_t first, size_t B,
 
 static int run_channel(pg_ctx *ctx, double ebn0_db, uint64_t first, size_t B, bool want_llr)
 {
-    return run_channel_to(ctx, ebn0_db, first, B, want_llr ? ctx->d_llr : nullptr, ctx->d_truth);
+    int rc = run_channel_to(ctx, ebn0_db, first, B, want_llr ? ctx->d_llr : nullptr, ctx->d_truth);
+    if (!rc && want_llr && ctx->p.llr_clip > 0) {  // receiver model: clip what the channel delivered, in place
+        CU(launch_convert_llr(ctx->d_llr, ctx->f64 ? PG_LLR_F64 : PG_LLR_F32, ctx->d_llr, ctx->f64, B * (size_t)ctx->p.N, ctx->st, ctx->p.llr_clip));
+        ctx->launches++;
+    }
+    return rc;
 }
 
 // decode B frames on stream `st` with at most `grid_cap` CTAs that use the scratch slots [cta_off, cta_off + grid_cap)
@@ -560,10 +566,10 @@ extern "C" int pg_decode_llr_device(pg_ctx *ctx, const void *d_llr, int llr_is_f
     if (B == 0) return PG_OK;
     CU(cudaSetDevice(ctx->p.device));
     const void *src = d_llr;
-    if (llr_is_f64 != (ctx->f64 ? PG_LLR_F64 : PG_LLR_F32)) {
+    if (llr_is_f64 != (ctx->f64 ? PG_LLR_F64 : PG_LLR_F32) || ctx->p.llr_clip > 0) {
         int rc = ensure_capacity(ctx, B);
         if (rc) return rc;
-        CU(launch_convert_llr(d_llr, llr_is_f64, ctx->d_llr, ctx->f64, B * (size_t)ctx->p.N, ctx->st));
+        CU(launch_convert_llr(d_llr, llr_is_f64, ctx->d_llr, ctx->f64, B * (size_t)ctx->p.N, ctx->st, ctx->p.llr_clip));
         ctx->launches++;
         src = ctx->d_llr;
     }
@@ -577,6 +583,13 @@ extern "C" int pg_decode_count_device(pg_ctx *ctx, const void *d_llr, int llr_is
     if (B == 0) return PG_OK;
     CU(cudaSetDevice(ctx->p.device));
     if (llr_is_f64 != (ctx->f64 ? PG_LLR_F64 : PG_LLR_F32)) { ctx->err = "pg_decode_count_device: LLR type must be the context's arithmetic type"; return PG_ERR_ARG; }
+    if (ctx->p.llr_clip > 0) {  // the caller's buffer stays untouched: clipped copy in the context's work buffer
+        int rc = ensure_capacity(ctx, B);
+        if (rc) return rc;
+        CU(launch_convert_llr(d_llr, llr_is_f64, ctx->d_llr, ctx->f64, B * (size_t)ctx->p.N, ctx->st, ctx->p.llr_clip));
+        ctx->launches++;
+        d_llr = ctx->d_llr;
+    }
     return run_decode(ctx, d_llr, B, d_truth_packed, d_u_hat_packed, d_frame_info, true);
 }
 
@@ -612,7 +625,7 @@ static int decode_host(pg_ctx *ctx, const void *llr, int llr_is_f64, size_t B, u
     CU(cudaSetDevice(ctx->p.device));
     const size_t N = ctx->p.N, W = ctx->W;
     const size_t esz = llr_esz(llr_is_f64);
-    const bool conv = llr_is_f64 != (ctx->f64 ? PG_LLR_F64 : PG_LLR_F32);
+    const bool conv = llr_is_f64 != (ctx->f64 ? PG_LLR_F64 : PG_LLR_F32) || ctx->p.llr_clip > 0;
     // Chunk = what one launch keeps resident.  A wave-sized launch runs all its warps in lockstep through the same phases of the
     // schedule (memory-heavy top layers, then leaf-heavy stretches), which costs the list kernel ~15 %; four quarter-grid launches on
     // four streams, offset by a quarter chunk each, interleave those phases and quarter the pipeline fill
@@ -640,7 +653,7 @@ static int decode_host(pg_ctx *ctx, const void *llr, int llr_is_f64, size_t B, u
                 CU(cudaMemcpyAsync(dst, (const char *)llr + off * N * esz, b * N * esz, cudaMemcpyHostToDevice, ctx->st_copy));
                 CU(cudaEventRecord(ctx->ev_h2d[s], ctx->st_copy));
                 CU(cudaStreamWaitEvent(cs, ctx->ev_h2d[s], 0));
-                if (conv) { CU(launch_convert_llr(ctx->p_in[s], llr_is_f64, ctx->p_llr[s], ctx->f64, b * N, cs)); ctx->launches++; }
+                if (conv) { CU(launch_convert_llr(ctx->p_in[s], llr_is_f64, ctx->p_llr[s], ctx->f64, b * N, cs, ctx->p.llr_clip)); ctx->launches++; }
                 int rc2 = run_decode_on(ctx, cs, lane_grid, lane * lane_grid, ctx->p_llr[s], b, nullptr, ctx->p_uhat[s], ctx->p_info[s], nullptr);
                 if (rc2) return rc2;
                 if (u_hat) {
@@ -668,7 +681,7 @@ static int decode_host(pg_ctx *ctx, const void *llr, int llr_is_f64, size_t B, u
             if (rc) return rc;
             void *dst = conv ? ctx->d_in : ctx->d_llr;
             CU(cudaMemcpyAsync(dst, (const char *)llr + off * N * esz, b * N * esz, cudaMemcpyHostToDevice, ctx->st));
-            if (conv) { CU(launch_convert_llr(ctx->d_in, llr_is_f64, ctx->d_llr, ctx->f64, b * N, ctx->st)); ctx->launches++; }
+            if (conv) { CU(launch_convert_llr(ctx->d_in, llr_is_f64, ctx->d_llr, ctx->f64, b * N, ctx->st, ctx->p.llr_clip)); ctx->launches++; }
             rc = run_decode(ctx, ctx->d_llr, b, nullptr, ctx->d_uhat, ctx->d_info, false);
             if (rc) return rc;
             if (u_hat) {
@@ -703,7 +716,7 @@ extern "C" int pg_decode_llr_counted(pg_ctx *ctx, const void *llr, int llr_is_f6
     CU(cudaSetDevice(ctx->p.device));
     const size_t N = ctx->p.N, W = ctx->W;
     const size_t esz = llr_esz(llr_is_f64);
-    const bool conv = llr_is_f64 != (ctx->f64 ? PG_LLR_F64 : PG_LLR_F32);
+    const bool conv = llr_is_f64 != (ctx->f64 ? PG_LLR_F64 : PG_LLR_F32) || ctx->p.llr_clip > 0;
     std::vector<uint32_t> packed;
     for (size_t off = 0; off < B; off += ctx->chunk_max) {
         const size_t b = std::min(ctx->chunk_max, B - off);
@@ -716,7 +729,7 @@ extern "C" int pg_decode_llr_counted(pg_ctx *ctx, const void *llr, int llr_is_f6
         CU(cudaMemcpyAsync(ctx->d_truth, packed.data(), b * W * 4, cudaMemcpyHostToDevice, ctx->st));
         void *dst = conv ? ctx->d_in : ctx->d_llr;
         CU(cudaMemcpyAsync(dst, (const char *)llr + off * N * esz, b * N * esz, cudaMemcpyHostToDevice, ctx->st));
-        if (conv) { CU(launch_convert_llr(ctx->d_in, llr_is_f64, ctx->d_llr, ctx->f64, b * N, ctx->st)); ctx->launches++; }
+        if (conv) { CU(launch_convert_llr(ctx->d_in, llr_is_f64, ctx->d_llr, ctx->f64, b * N, ctx->st, ctx->p.llr_clip)); ctx->launches++; }
         CU(cudaMemsetAsync(ctx->d_cnt2, 0, CNT_N * 8, ctx->st));
         rc = run_decode_dev(ctx, ctx->d_llr, b, ctx->d_truth, ctx->d_uhat, ctx->d_info, ctx->d_cnt2);
         if (rc) return rc;

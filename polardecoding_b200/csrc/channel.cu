@@ -185,15 +185,18 @@ cudaError_t launch_channel(const ChannelArgs &a, bool f64, int sm_count, cudaStr
 }
 
 // ---------------------------------------------------------------- small helpers
+// LLR ingest: element type conversion (float / double / half -> the decoder's arithmetic type) and the optional clipping
+// (pg_params.llr_clip > 0) in one pass.  Source and destination may be the same buffer when the types are equal.
+template <typename D> __device__ __forceinline__ D clip_to(D v, D c) { return (c > (D)0) ? ((v > c) ? c : ((v < -c) ? -c : v)) : v; }
 template <typename S, typename D>
-__global__ void convert_kernel(const S *__restrict__ s, D *__restrict__ d, size_t n)
+__global__ void convert_kernel(const S *s, D *d, size_t n, D clip)
 {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) d[i] = (D)s[i];
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) d[i] = clip_to<D>((D)s[i], clip);
 }
 
-// packed-half LLRs (PG_LLR_F16: half the host-to-device bytes of a streamed frame) to the decoder's arithmetic type, 8 values per thread step
+// packed-half LLRs (PG_LLR_F16: half the host-to-device bytes of a streamed frame), 8 values per thread step
 template <typename D>
-__global__ void convert_h_kernel(const uint4 *__restrict__ s, D *__restrict__ d, size_t n8, const __half *__restrict__ tail_s, size_t n)
+__global__ void convert_h_kernel(const uint4 *__restrict__ s, D *__restrict__ d, size_t n8, const __half *__restrict__ tail_s, size_t n, D clip)
 {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
         const uint4 v = s[i];
@@ -201,29 +204,32 @@ __global__ void convert_h_kernel(const uint4 *__restrict__ s, D *__restrict__ d,
 #pragma unroll
         for (int e = 0; e < 4; e++) {
             const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&w[e]));
-            d[i * 8 + 2 * e] = (D)f.x;
-            d[i * 8 + 2 * e + 1] = (D)f.y;
+            d[i * 8 + 2 * e] = clip_to<D>((D)f.x, clip);
+            d[i * 8 + 2 * e + 1] = clip_to<D>((D)f.y, clip);
         }
     }
     if (blockIdx.x == 0)
-        for (size_t i = n8 * 8 + threadIdx.x; i < n; i += blockDim.x) d[i] = (D)__half2float(tail_s[i]);
+        for (size_t i = n8 * 8 + threadIdx.x; i < n; i += blockDim.x) d[i] = clip_to<D>((D)__half2float(tail_s[i]), clip);
 }
 
-// src_fmt: 0 float, 1 double, 2 half (include/polargpu.h PG_LLR_*)
-cudaError_t launch_convert_llr(const void *src, int src_fmt, void *dst, bool dst_f64, size_t count, cudaStream_t st)
+// src_fmt: 0 float, 1 double, 2 half (include/polargpu.h PG_LLR_*); clip <= 0: no clipping (then src_fmt must differ from the destination type)
+cudaError_t launch_convert_llr(const void *src, int src_fmt, void *dst, bool dst_f64, size_t count, cudaStream_t st, double clip)
 {
     if (count == 0) return cudaSuccess;
     const int threads = 256;
     size_t blocks = (count + threads - 1) / threads;
     if (blocks > 148 * 32) blocks = 148 * 32;
-    if (src_fmt == 1 && !dst_f64) convert_kernel<double, float><<<(unsigned)blocks, threads, 0, st>>>((const double *)src, (float *)dst, count);
-    else if (src_fmt == 0 && dst_f64) convert_kernel<float, double><<<(unsigned)blocks, threads, 0, st>>>((const float *)src, (double *)dst, count);
-    else if (src_fmt == 2) {
+    const unsigned g = (unsigned)blocks;
+    if (src_fmt == 2) {
         const size_t n8 = count / 8;
-        blocks = std::max<size_t>(1, std::min<size_t>((n8 + threads - 1) / threads, 148 * 16));
-        if (dst_f64) convert_h_kernel<double><<<(unsigned)blocks, threads, 0, st>>>((const uint4 *)src, (double *)dst, n8, (const __half *)src, count);
-        else convert_h_kernel<float><<<(unsigned)blocks, threads, 0, st>>>((const uint4 *)src, (float *)dst, n8, (const __half *)src, count);
-    } else return cudaErrorInvalidValue;
+        const unsigned gh = (unsigned)std::max<size_t>(1, std::min<size_t>((n8 + threads - 1) / threads, 148 * 16));
+        if (dst_f64) convert_h_kernel<double><<<gh, threads, 0, st>>>((const uint4 *)src, (double *)dst, n8, (const __half *)src, count, clip);
+        else convert_h_kernel<float><<<gh, threads, 0, st>>>((const uint4 *)src, (float *)dst, n8, (const __half *)src, count, (float)clip);
+    } else if (src_fmt == 1 && !dst_f64) convert_kernel<double, float><<<g, threads, 0, st>>>((const double *)src, (float *)dst, count, (float)clip);
+    else if (src_fmt == 0 && dst_f64) convert_kernel<float, double><<<g, threads, 0, st>>>((const float *)src, (double *)dst, count, clip);
+    else if (clip > 0 && src_fmt == 0) convert_kernel<float, float><<<g, threads, 0, st>>>((const float *)src, (float *)dst, count, (float)clip);
+    else if (clip > 0 && src_fmt == 1) convert_kernel<double, double><<<g, threads, 0, st>>>((const double *)src, (double *)dst, count, clip);
+    else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }
 

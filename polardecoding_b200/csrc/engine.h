@@ -83,7 +83,8 @@ cudaError_t bp_h2_plan(int n, BpPlan *plan);
 cudaError_t launch_bp_h2(const BpArgs &a, int n, int grid, cudaStream_t st);
 
 // ---------------------------------------------------------------- helpers
-cudaError_t launch_convert_llr(const void *src, int src_fmt /* 0 float, 1 double, 2 half */, void *dst, bool dst_f64, size_t count, cudaStream_t st);
+cudaError_t launch_convert_llr(const void *src, int src_fmt /* 0 float, 1 double, 2 half */, void *dst, bool dst_f64, size_t count, cudaStream_t st,
+                               double clip = 0.0 /* > 0: clip to [-clip, clip]; then src and dst may be the same type / buffer */);
 cudaError_t launch_unpack_bits(const uint32_t *packed, uint8_t *bytes, size_t frames, int N, cudaStream_t st);
 
 }  // namespace polar

@@ -316,6 +316,7 @@ int main(int argc, char **argv)
     long long seed = -1, maxf = 0;
     int use_ref = 0, real = -1, early = 0, verbose = 0;
     const char *crc_file = NULL;
+    double llr_clip = 0;
     if (!name[0]) { const char *b = strrchr(argv[0], '/'); name = b ? b + 1 : argv[0]; }
     for (int i = 1; i < argc; i++) {
         const char *a = argv[i], *v = (i + 1 < argc) ? argv[i + 1] : NULL;
@@ -333,6 +334,7 @@ int main(int argc, char **argv)
         else if (!strcmp(a, "--iters") && v) { iters = atol(v); i++; }
         else if (!strcmp(a, "--gpus") && v) { gpus = atol(v); i++; }
         else if (!strcmp(a, "--crc-file") && v) { crc_file = v; i++; }
+        else if (!strcmp(a, "--llr-clip") && v) { llr_clip = atof(v); i++; }
         else if (!strcmp(a, "--early-stop")) early |= 1;
         else if (!strcmp(a, "--gmatrix-stop")) early |= 2;
         else if (!strcmp(a, "--verbose")) verbose = 1;
@@ -356,6 +358,7 @@ int main(int argc, char **argv)
         p.crc_poly = poly;
     }
     p.bp_early_stop = early;
+    p.llr_clip = (float)llr_clip;
     p.real = (real >= 0) ? real : (use_ref ? PG_REAL_F64 : PG_REAL_F32);
     if (e0 < 0) { e0 = pd->e0; e1 = pd->e1; }
     if (ble < 0) ble = maxf ? 0 : pd->ble;

@@ -397,3 +397,45 @@ def test_fp16_llr_input(prog, ebn0, B):
     d1, _ = eng.decode_llr(h[:3, :], packed=True)
     assert (d1 == d16[:3]).all()
     eng.close()
+
+
+@pytest.mark.parametrize("prog,B,ebn0", [("CASCL_128", 200, 2.0), ("BP_128", 64, 2.0), ("SC_1024", 64, 2.0), ("CASCL_1024_L8", 24, 1.5)])
+def test_llr_clip(prog, B, ebn0):
+    """pg_params.llr_clip (optional receiver model; not in the reference): decoding with clipping c must equal the
+    reference decoder run on LLRs clipped to [-c, c] -- through the host path (same-type and converting ingest), the device path
+    and the fused channel path; a clip far above every LLR changes nothing."""
+    import torch
+    from polardecoding_b200 import Engine
+    o = Oracle(prog)
+    u, llr = frames(o, B, ebn0, seed=77)
+    c = 3.0
+    want, _ = o.decode(np.clip(llr, -c, c))
+    eng = Engine(prog, real="f64", llr_clip=c)
+    got, flags = eng.decode_llr(llr)                                   # fp64 in, fp64 context: clip-only ingest pass
+    assert (got == want).all(), describe(got, want, flags)
+    l32 = llr.astype(np.float32)
+    want32, _ = o.decode(np.clip(l32.astype(np.float64), -c, c))
+    got32, flags = eng.decode_llr(l32)                                 # converting ingest pass
+    assert (got32 == want32).all(), describe(got32, want32, flags)
+    d_llr = torch.from_numpy(llr).cuda()
+    d_out = torch.zeros((B, o.N // 32), dtype=torch.int32, device="cuda")
+    eng.decode_llr_device(d_llr.data_ptr(), True, B, d_out.data_ptr(), None)
+    eng.sync()
+    assert (d_llr.cpu().numpy() == llr).all()                          # the caller's buffer is not modified
+    bits = ((d_out.cpu().numpy().view(np.uint32)[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(B, o.N)
+    assert (bits == want * o.inI[None, :]).all()
+    eng.close()
+    plain = Engine(prog, real="f64")
+    far = Engine(prog, real="f64", llr_clip=1e6)
+    a, _ = plain.decode_llr(llr)
+    b, _ = far.decode_llr(llr)
+    assert (a == b).all()
+    # fused channel path: the same frames with and without clipping are the same frames (counts differ only through the decoder)
+    acc0, _ = plain.simulate_batch(ebn0, 0, 2000)
+    e2 = Engine(prog, real="f64", llr_clip=c)
+    acc1, fe = e2.simulate_batch(ebn0, 0, 2000, want_frame_err=True)
+    llr_c, u_c = e2.channel(ebn0, 0, 64)                               # pg_channel returns what the decoder is fed: clipped
+    assert np.abs(llr_c).max() <= c and acc1.frames == acc0.frames == 2000
+    dec, _ = e2.decode_llr(llr_c)
+    assert (((dec != u_c) & (e2.inI[None, :] > 0)).sum(1)[:64] == fe[:64]).all()
+    plain.close(); far.close(); e2.close()
