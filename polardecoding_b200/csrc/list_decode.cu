@@ -188,14 +188,18 @@ __device__ __forceinline__ void prefetch_l1(const void *p)
     (void)p;
 #endif
 }
-// Measured (CA-SCL 1024 L=8, fp32 / fp64 M frames/s): fused g+f layers 12.72 / 5.31 against 13.54 / 6.08 without -- the fused loop
-// keeps sixteen operand registers in flight on top of the four CHKs, so the compiler re-derives its addresses every step: +6 % executed
-// instructions for -12 % HBM reads and long_scoreboard 3.1 -> 2.25 per issue; the issue slots are worth more than the stalls.
+// Two more ways to keep the f-layer from re-reading a g-layer's output out of HBM were measured and are slower (CA-SCL 1024 L=8, fp32
+// M frames/s, product 13.5): the g-layer fused with the f-layer below it (registers instead of a scratch round trip; 12.7, +6 %
+// instructions; removed again, see profiles/r2_list_kernel_experiments.md) and the chunked chain below (POLAR_CHUNK: 12.7, HBM reads -13 %,
+// long_scoreboard 3.0 -> 2.3 per issue, +7 % instructions).  The issue slots are worth more than the stalls.
+#ifndef POLAR_CHUNK
+#define POLAR_CHUNK 0        // > 0 (a multiple of 8): g-layers at stages >= POLAR_CHUNK_MIN are produced this many rows per half at a time, each
+#endif                       // chunk consumed at once by the f-layer below (chunked chain, see the main loop)
+#ifndef POLAR_CHUNK_MIN
+#define POLAR_CHUNK_MIN 7
+#endif
 #ifndef POLAR_F32_CTAS
 #define POLAR_F32_CTAS 32   // resident one-warp CTAs per SM the fp32 kernel is compiled for (64 registers per thread)
-#endif
-#ifndef POLAR_FUSE_GF
-#define POLAR_FUSE_GF 0  // g-layers at stages >= 5 run fused with the f-layer below them (see gf_layer): 0 never, 1 always, 2 fp64 only
 #endif
 // fewer inline copies of the leaf body / of the four-CHK block in the hot loop (instruction cache): 0 never, 1 always, 2 fp64 only
 #ifndef POLAR_FOLD_LEAF
@@ -289,7 +293,6 @@ list_decode_kernel(const ListArgs a)
     constexpr bool HAS_TM = C::HAS_TM;
     constexpr bool FOLD_LEAF = POLAR_FOLD_LEAF == 1 || (POLAR_FOLD_LEAF == 2 && sizeof(real) == 8);
     constexpr bool FOLD_F3 = POLAR_FOLD_F3 == 1 || (POLAR_FOLD_F3 == 2 && sizeof(real) == 8);
-    constexpr bool FUSE_GF = POLAR_FUSE_GF == 1 || (POLAR_FUSE_GF == 2 && sizeof(real) == 8);
     constexpr int PWID = PW::W;
     constexpr ptr_t PMASK = (ptr_t)((1u << PWID) - 1);
     constexpr uint32_t LMASK = (L == 32) ? 0xffffffffu : ((1u << (L & 31)) - 1u);  // lanes of one frame
@@ -363,7 +366,7 @@ list_decode_kernel(const ListArgs a)
         // ---- f-layer producing stage s (4 <= s < LOGN) from stage s+1, into the HOME array -----------------
         // An f-layer always follows the layer that produced stage s+1 in the same chain, so its source is this lane's own
         // home array (or the channel): no pointer lookup.  Pointer fields are set once per chain (set_pfields).
-        auto f_layer = [&](int s, bool coop) {
+        auto f_layer = [&](int s, bool coop, int r0 = 0, int rn = -1) {   // rows r0 .. r0+rn-1 of the output (default: all)
             const int cnt4 = 1 << (s - 2);
             if (coop) {
                 // all lanes of the frame still hold the same path (no information bit yet): they split the layer and
@@ -396,21 +399,22 @@ list_decode_kernel(const ListArgs a)
             };
             // scratch / channel operands come from L2 or HBM: fetch the next pair while the current four CHKs run
             V4 x, y, x1, y1;
-            load2(0, x, y);
+            const int rend = (rn < 0) ? cnt4 : r0 + rn;
+            load2(r0, x, y);
 #pragma unroll 1
-            for (int i4 = 0; i4 < cnt4; i4 += 2) {  // cnt4 >= 4 here; two steps per trip so that the operand registers ping-pong
+            for (int i4 = r0; i4 < rend; i4 += 2) {  // an even number of rows; two steps per trip so that the operand registers ping-pong
                 load2(i4 + 1, x1, y1);
                 store(i4, f4<real>(x, y));
-                if (i4 + 2 < cnt4) load2(i4 + 2, x, y);
+                if (i4 + 2 < rend) load2(i4 + 2, x, y);
                 store(i4 + 1, f4<real>(x1, y1));
             }
             if (tdst) tm_wait_st();
         };
 
         // ---- g-layer producing stage t (4 <= t < LOGN) from stage t+1 (via the pointer word) and the partial sums B[t]
-        auto g_layer = [&](int t) {
+        auto g_layer = [&](int t, int r0 = 0, int rn = -1) {   // rows r0 .. r0+rn-1 of the output (a multiple of 8, r0 too; default: all)
             const int cnt4 = 1 << (t - 2);
-            const uint32_t *bsrc = (t >= 6) ? bits_at(t) + fbase + bfield(t) : nullptr;
+            const uint32_t *bsrc = (t >= 6) ? bits_at(t) + fbase + bfield(t) + (r0 >> 3) * 32 : nullptr;
             uint32_t bw = (t == 4) ? ((Blow >> 12) & 0xFFFFu) : B5;
             // one loop body for every storage class.  Tensor-memory source: a lane reaches its own row only, so every lane loads
             // its OWN row and the values of the slot the pointer word names arrive by shuffle.
@@ -422,10 +426,12 @@ list_decode_kernel(const ListArgs a)
             int stride = 1;
             if (!tsrc && t + 1 != LOGN) { src = stage_at(t + 1) + fbase + pfield(t + 1); stride = 32; }
             const V4 *src2 = src + cnt4 * stride;
+            if (r0) { src += r0 * stride; src2 += r0 * stride; if (!tdst) dst += r0 * 32; }
+            const int bend = ((rn < 0) ? cnt4 : r0 + rn) >> 2;
             // a g-layer is one add per node: memory bound (its operands come from the L2/HBM scratch).  Batches of four
             // node groups: eight independent 128-bit loads in flight per lane, 16 partial-sum bits per batch.
 #pragma unroll 1
-            for (int b = 0; b < (cnt4 >> 2); b++) {
+            for (int b = r0 >> 2; b < bend; b++) {
                 if (t >= 6 && !(b & 1)) { bw = *bsrc; bsrc += 32; }
                 V4 up[4], lo[4];
                 if (tsrc) {
@@ -450,35 +456,6 @@ list_decode_kernel(const ListArgs a)
                 bw >>= 16;
             }
             if (tdst) tm_wait_st();
-        };
-
-        // ---- g-layer at stage t (t >= 5) FUSED with the f-layer below it ---------------------------------------------------
-        // The f-layer at t-1 pairs node i with node i + h (h = half of stage t), so one step loads the four source groups of those
-        // two g-outputs, stores them (the g-layer that opens stage t-1 half a block later reads them again) and feeds them to the
-        // four CHKs from registers: the f-layer does not re-read stage t, and the memory latency of the g-layer -- one add per node,
-        // 23 % of the warp samples at 8 % of the instructions as a loop of its own -- hides behind the CHKs of the previous step.
-        auto gf_layer = [&](int t) {
-            const int h = 1 << (t - 3);              // V4 groups per half of stage t = outputs of the f-layer
-            V4 *dg = stage_at(t) + lane, *df = stage_at(t - 1) + lane;
-            const V4 *src = ch4;
-            int stride = 1;
-            if (t + 1 != LOGN) { src = stage_at(t + 1) + fbase + pfield(t + 1); stride = 32; }
-            const int oh = h * stride;               // element offsets of the three other source groups of a step
-            const uint32_t *bsrc = (t >= 6) ? bits_at(t) + fbase + bfield(t) : nullptr;
-            uint32_t w0 = B5, w1 = B5 >> 16;         // t == 5: B[5] is a register (nibbles 0..3 and 4..7)
-            V4 a0 = ldv(src), a1 = ldv(src + 2 * oh), b0 = ldv(src + oh), b1 = ldv(src + 3 * oh);
-#pragma unroll 1
-            for (int i = 0; i < h; i++, dg += 32, df += 32) {
-                if (t >= 6 && (i & 7) == 0) { w0 = bsrc[(i >> 3) * 32]; w1 = bsrc[((i + h) >> 3) * 32]; }
-                const V4 gi = g4<real>(a0, a1, w0 & 0xFu), gh = g4<real>(b0, b1, w1 & 0xFu);
-                w0 >>= 4; w1 >>= 4;
-                // operands of the next step (the last step re-reads its own: an unconditional load keeps the loop body straight)
-                if (i + 1 < h) src += stride;
-                a0 = ldv(src); a1 = ldv(src + 2 * oh); b0 = ldv(src + oh); b1 = ldv(src + 3 * oh);
-                stv(dg, gi);
-                stv(dg + h * 32, gh);
-                stv(df, f4<real>(gi, gh));
-            }
         };
 
         // ---- two g-outputs of the top stages are VIRTUAL: never stored, recomputed where they are consumed ----------------
@@ -785,6 +762,29 @@ list_decode_kernel(const ListArgs a)
                 } else {       // a longer chain: g at the stage the finished block opens, f-layers down to stage 4, f at stage 3
                     int s = LOGN - 1;
                     top = s;
+                    if (POLAR_CHUNK > 0 && !POLAR_VIRT && !HAS_TM && FOLD_F3) {
+                        // Chunked chain: the g-layer at stage t is produced POLAR_CHUNK rows of each half at a time and the f-layer below
+                        // consumes those rows at once, while they are still in the L2 (a whole top g-layer takes a warp ~200 us, the L2
+                        // keeps a line ~30 us: the unchunked f-layer re-reads everything from HBM).  One call site per loop body.
+                        int t = 0;                                  // stage of the g-layer that opens the chain (0: none, leaf 0)
+                        if (j4 != 0) { t = __ffs(j4) - 1 + 2; top = t; s = t - 1; }
+                        const int h = (t >= 5) ? (1 << (t - 3)) : 0;   // rows per half of stage t = rows of the f-layer at t-1
+                        const int c = (t >= POLAR_CHUNK_MIN && h > POLAR_CHUNK) ? POLAR_CHUNK : 0;   // 0: whole layers
+                        int r0 = 0, ph = (t == 0) ? 2 : 0;
+                        while (s >= 3) {
+                            if (ph < 2) {                            // g rows: c of each half, or the whole layer
+                                g_layer(t, c ? r0 + ph * h : 0, c ? c : -1);
+                                ph = c ? ph + 1 : 2;
+                                continue;
+                            }
+                            const bool part = c && s == t - 1;
+                            f_layer(s, false, part ? r0 : 0, part ? c : -1);
+                            if (part && r0 + c < h) { r0 += c; ph = 0; continue; }
+                            s--;
+                        }
+                        ld_own2(3, 0, 1, a3, b3);
+                        stored3 = true;
+                    } else {
                     if (j4 != 0) {
                         s = __ffs(j4) - 1 + 2;
                         top = s;
@@ -800,9 +800,6 @@ list_decode_kernel(const ListArgs a)
                         } else if (virt && s == LOGN - 3 && j4 == 3 * (N >> 5)) {  // leaf 3N/8: g-layer at S-1 from the virtual block 1 of S
                             g_virtual(s, 1);
                             s--;
-                        } else if (FUSE_GF && !HAS_TM && s >= 5) {   // g-layer fused with the f-layer below it
-                            gf_layer(s);
-                            s -= 2;
                         } else {
                             g_layer(s);
                             s--;
@@ -821,6 +818,7 @@ list_decode_kernel(const ListArgs a)
                         a3 = f4<real>(u, l);
                         ld_own2(4, 1, 3, u, l);
                         b3 = f4<real>(u, l);
+                    }
                     }
                 }
                 if (stored3) {

@@ -62,7 +62,11 @@ extern "C" int emu_list_decode(int n, int L, int f64, const void *llr, unsigned 
     int rc = -1;
 #define X(NN, LL) \
     if (n == NN && L == LL) rc = f64 ? run_case<double, NN, LL>(a, grid, scratch, tm) : run_case<float, NN, LL>(a, grid, scratch, tm);
+#ifdef EMU_FEW   // option flavours of the build (tests/emu_lib.py FLAVORS) only need the configurations their tests use
+    X(9, 8) X(10, 1) X(10, 8)
+#else
     X(5, 1) X(5, 4) X(6, 8) X(7, 1) X(7, 2) X(7, 8) X(7, 32) X(8, 4) X(9, 8) X(9, 16) X(10, 1) X(10, 2) X(10, 8) X(10, 16) X(10, 32)
+#endif
 #undef X
     if (collectives) *collectives = emu::g.collectives;
     return rc;

@@ -8,20 +8,23 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EMU_DIR = os.path.join(ROOT, "tests", "emu")
-EMU_SO = os.path.join(EMU_DIR, "_build", "libpolar_emu.so")
+FLAVORS = {"": "", "chunk": "-DPOLAR_VIRT=0 -DPOLAR_CHUNK=8 -DEMU_FEW"}   # build flavour -> extra compile options (see tests/emu/Makefile)
 
-_lib = None
+_libs = {}
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        subprocess.check_call(["make", "-C", EMU_DIR, "-j4"], stdout=subprocess.DEVNULL)
-        _lib = C.CDLL(EMU_SO)
+def lib(flavor=""):
+    if flavor not in _libs:
+        cmd = ["make", "-C", EMU_DIR, "-j4"]
+        if flavor:
+            cmd += ["FLAVOR=" + flavor, "EMU_EXTRA=" + FLAVORS[flavor]]
+        subprocess.check_call(cmd, stdout=subprocess.DEVNULL)
+        l = C.CDLL(os.path.join(EMU_DIR, "_build" + ("_" + flavor if flavor else ""), "libpolar_emu.so"))
         vp = C.c_void_p
-        _lib.emu_list_decode.argtypes = [C.c_int, C.c_int, C.c_int, vp, C.c_ulonglong, vp, vp, vp, C.c_int, C.c_int, C.c_int,
-                                         C.c_uint, vp, vp, vp, C.c_int]
-    return _lib
+        l.emu_list_decode.argtypes = [C.c_int, C.c_int, C.c_int, vp, C.c_ulonglong, vp, vp, vp, C.c_int, C.c_int, C.c_int,
+                                      C.c_uint, vp, vp, vp, C.c_int]
+        _libs[flavor] = l
+    return _libs[flavor]
 
 
 def crc_masks(I, N, r, poly):
@@ -43,7 +46,7 @@ def crc_masks(I, N, r, poly):
     return m
 
 
-def list_decode(oracle, llr, L, use_crc, f64=True, grid=1, coop=True, count_from=0, tm=1):
+def list_decode(oracle, llr, L, use_crc, f64=True, grid=1, coop=True, count_from=0, tm=1, flavor=""):
     """Decode llr (B,N) with the emulated list kernel; oracle supplies the code (I, inI, r, crc_poly).
     tm: 0 = layout without tensor memory, 1 = the dispatcher's choice, 2 / 3 = a tensor-memory layout forced for any type (stages 3..5 / stage 6 only; N >= 256).
     -> (u_hat (B,N) int32, frame_info (B,) uint32, collectives executed)"""
@@ -63,7 +66,7 @@ def list_decode(oracle, llr, L, use_crc, f64=True, grid=1, coop=True, count_from
     out = np.zeros((B, W), dtype=np.uint32)
     fi = np.zeros(B, dtype=np.uint32)
     coll = C.c_ulonglong(0)
-    rc = lib().emu_list_decode(n, L, int(f64), llr.ctypes.data, B, info.ctypes.data, cnt.ctypes.data, masks.ctypes.data, oracle.r,
+    rc = lib(flavor).emu_list_decode(n, L, int(f64), llr.ctypes.data, B, info.ctypes.data, cnt.ctypes.data, masks.ctypes.data, oracle.r,
                                int(use_crc), (first // 4) if coop else 0, grid, out.ctypes.data, fi.ctypes.data, C.byref(coll), tm)
     assert rc == 0, "configuration (n=%d, L=%d, tm=%d) is not compiled into the emulator (rc %d)" % (n, L, tm, rc)
     bits = ((out[:, :, None] >> np.arange(32, dtype=np.uint32)[None, None, :]) & 1).reshape(B, N).astype(np.int32)

@@ -99,3 +99,16 @@ def test_emulated_fp32_tensor_memory_kernel_equals_plain_fp32_kernel(prog, L, cr
     a, fa, _ = emu_lib.list_decode(o, llr, L, crc, f64=False, grid=2, tm=0)
     b, fb, _ = emu_lib.list_decode(o, llr, L, crc, f64=False, grid=1, tm=2)
     assert (a == b).all() and (fa == fb).all()
+
+
+@pytest.mark.parametrize("prog,L,crc,B,snr", [("CASCL_1024_L8", 8, 1, 6, 1.0), ((1024, 1000), 8, 0, 4, 4.0), ((512, 300), 8, 0, 6, 2.0), ("SC_1024", 1, 0, 33, 1.5)])
+def test_emulated_chunked_chain_equals_oracle_f64(prog, L, crc, B, snr):
+    """the optional chunked chain (-DPOLAR_CHUNK=8: top g-layers produced eight rows per half at a time, each chunk consumed at once by
+    the f-layer below; off in the product) in a second emulator build: same decisions as the oracle"""
+    o = Oracle(prog) if isinstance(prog, str) else Oracle(N=prog[0], K=prog[1], L=L)
+    llr = awgn_llr(np.random.default_rng(17 + B), o.N, B, snr)
+    want, aux = o.decode(llr, kind=("sc" if L == 1 else ("cascl" if crc else "scl")), L=L)
+    got, fi, _ = emu_lib.list_decode(o, llr, L, crc, f64=True, grid=2, tm=0, flavor="chunk")
+    assert (got == want * o.inI[None, :]).all()
+    if L > 1:
+        assert (((fi >> 16) & 3) == aux).all()
