@@ -383,12 +383,13 @@ list_decode_kernel(const ListArgs a)
             // one loop body for every storage class (see f4): the source is this lane's home array in the scratch / shared memory,
             // the channel, or its own tensor-memory row; the destination its home array or its tensor-memory row
             const bool tsrc = in_tm(s + 1), tdst = in_tm(s);
-            const int osrc = tmoff(s + 1), odst = tmoff(s);
-            V4 *dst = tdst ? nullptr : stage_at(s) + lane;
+            const int osrc = tmoff(s + 1) + r0, odst = tmoff(s) + r0;
+            V4 *dst = tdst ? nullptr : stage_at(s) + lane + r0 * 32;
             const V4 *src = ch4;
             int stride = 1;
             if (!tsrc && s + 1 != LOGN) { src = stage_at(s + 1) + lane; stride = 32; }
-            const V4 *src2 = src + cnt4 * stride;
+            const V4 *src2 = src + (cnt4 + r0) * stride;   // the row range is folded into the bases: the loop below counts from 0
+            src += r0 * stride;
             auto load2 = [&](int i4, V4 &x, V4 &y) {
                 if (tsrc) { x = tm_ld<real>(tm, osrc + i4); y = tm_ld<real>(tm, osrc + i4 + cnt4); tm_wait_ld(); }
                 else { x = ldv(src + i4 * stride); y = ldv(src2 + i4 * stride); }
@@ -399,13 +400,13 @@ list_decode_kernel(const ListArgs a)
             };
             // scratch / channel operands come from L2 or HBM: fetch the next pair while the current four CHKs run
             V4 x, y, x1, y1;
-            const int rend = (rn < 0) ? cnt4 : r0 + rn;
-            load2(r0, x, y);
+            const int rows = (rn < 0) ? cnt4 : rn;
+            load2(0, x, y);
 #pragma unroll 1
-            for (int i4 = r0; i4 < rend; i4 += 2) {  // an even number of rows; two steps per trip so that the operand registers ping-pong
+            for (int i4 = 0; i4 < rows; i4 += 2) {  // an even number of rows; two steps per trip so that the operand registers ping-pong
                 load2(i4 + 1, x1, y1);
                 store(i4, f4<real>(x, y));
-                if (i4 + 2 < rend) load2(i4 + 2, x, y);
+                if (i4 + 2 < rows) load2(i4 + 2, x, y);
                 store(i4 + 1, f4<real>(x1, y1));
             }
             if (tdst) tm_wait_st();
@@ -419,19 +420,19 @@ list_decode_kernel(const ListArgs a)
             // one loop body for every storage class.  Tensor-memory source: a lane reaches its own row only, so every lane loads
             // its OWN row and the values of the slot the pointer word names arrive by shuffle.
             const bool tsrc = in_tm(t + 1), tdst = in_tm(t);
-            const int osrc = tmoff(t + 1), odst = tmoff(t);
+            const int osrc = tmoff(t + 1) + r0, odst = tmoff(t) + r0;   // the row range is folded into the bases
             const int sl = fbase + pfield(t + 1);
-            V4 *dst = tdst ? nullptr : stage_at(t) + lane;
+            V4 *dst = tdst ? nullptr : stage_at(t) + lane + r0 * 32;
             const V4 *src = ch4;
             int stride = 1;
             if (!tsrc && t + 1 != LOGN) { src = stage_at(t + 1) + fbase + pfield(t + 1); stride = 32; }
-            const V4 *src2 = src + cnt4 * stride;
-            if (r0) { src += r0 * stride; src2 += r0 * stride; if (!tdst) dst += r0 * 32; }
-            const int bend = ((rn < 0) ? cnt4 : r0 + rn) >> 2;
+            const V4 *src2 = src + (cnt4 + r0) * stride;
+            src += r0 * stride;
+            const int bend = ((rn < 0) ? cnt4 : rn) >> 2;
             // a g-layer is one add per node: memory bound (its operands come from the L2/HBM scratch).  Batches of four
             // node groups: eight independent 128-bit loads in flight per lane, 16 partial-sum bits per batch.
 #pragma unroll 1
-            for (int b = r0 >> 2; b < bend; b++) {
+            for (int b = 0; b < bend; b++) {
                 if (t >= 6 && !(b & 1)) { bw = *bsrc; bsrc += 32; }
                 V4 up[4], lo[4];
                 if (tsrc) {
